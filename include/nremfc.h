@@ -1,0 +1,154 @@
+/* nremfc.h — C ABI of the B200-native Wilson-Cowan -> BOLD -> FC -> GoF hot path.
+ *
+ * Everything the reference does between "module attributes are set" and "one row of
+ * goodness-of-fit numbers exists" (netwWilsonCowanPlastic.py:77-158, whole_sweep_both.py:78-94,
+ * utils.py:42-50) is reachable through the entry points below.  The reference has no FFI of
+ * its own (it is Python + numba); each entry point names the reference call it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative nrem_status otherwise; the message of
+ *     the last failure on the calling thread is nrem_last_error().  No exceptions cross.
+ *   - all array arguments are DEVICE pointers (cudaMalloc'd / torch CUDA tensors) unless the
+ *     name starts with h_; outputs are caller-allocated; nothing is retained after return.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - row-major ("C order") everywhere; shapes are written [outer, ..., inner].
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     NREM_ERR_CUDA.
+ */
+#ifndef NREMFC_H
+#define NREMFC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NREM_ABI_VERSION 1
+
+typedef enum nrem_status {
+    NREM_OK = 0,
+    NREM_ERR_ARG = -1,      /* bad shape / null pointer / unsupported size */
+    NREM_ERR_CUDA = -2,     /* CUDA runtime error (no device, launch failure, ...) */
+    NREM_ERR_UNSUPPORTED = -3
+} nrem_status;
+
+/* Model constants — the module attributes of netwWilsonCowanPlastic.py:23-57 that
+ * wilsonCowan()/run() freeze at JIT time, plus the phase lengths len(timeTrans1),
+ * len(timeTrans2), len(timeSim) (netwWilsonCowanPlastic.py:48-50). */
+typedef struct nrem_wc_params {
+    double a_ee, a_ie_0, a_ei, a_ii;   /* :23-25 */
+    double tauE, tauI;                 /* :27 */
+    double P, rhoE;                    /* :29,:32 */
+    double rE, rI, mu, sigmaI;         /* :35-38 */
+    double dtSim, sqdtD;               /* :46,:56 */
+    double E0, I0;                     /* :90-91 */
+    double tau_ip[3];                  /* :101,:111,:118 */
+    int64_t n1, n2, n3;                /* Euler steps per phase */
+    int32_t downsamp;                  /* int(dt/dtSim), :120 */
+    int32_t nnodes;                    /* N = len(CM), :68 */
+    uint64_t seed;                     /* key of the counter-based noise stream */
+} nrem_wc_params;
+
+int nrem_abi_version(void);
+const char* nrem_last_error(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int nrem_device_count(void);
+
+/* ---- reference-shaped stages (float64) -------------------------------------------------- */
+
+/* Replaces run() (netwWilsonCowanPlastic.py:86-137) for B independent simulations, float64.
+ *   CM      [N,N]        structural connectivity
+ *   G,sigmaE [B,N]       per-simulation, per-node coupling gain and excitatory slope
+ *   streams [B]          replicate ids of the counter-based noise (ignored when noise != NULL)
+ *   noise   NULL, or [B or 1, n1+n2+n3, N] values to add inside the sigmoid (already scaled by
+ *           sqdtD — exactly what np.random.normal(0, sqdtD, N) returned at :80); noise_batch = 1
+ *           shares one stream between all B simulations.
+ *   Y       NULL or [B, nrec, 3, N]   state (E, I, a_ie) stored BEFORE step i when i % downsamp == 0
+ *   final   NULL or [B, 3, N]         state after the last step                                  */
+int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, const double* sigmaE,
+                    const uint64_t* streams, const double* noise, int noise_batch, int B, int64_t nrec,
+                    double* Y, double* final_state, void* stream);
+
+/* Replaces wilsonCowan(t, X, sigmaE, mu, tau_ip, G) (netwWilsonCowanPlastic.py:77-83): one
+ * derivative evaluation.  X [3,N], noise [N] (scaled), G/sigmaE [N] -> dX [3,N].            */
+int nrem_wc_derivative_f64(const nrem_wc_params* p, const double* CM, const double* X, const double* G,
+                           const double* sigmaE, const double* noise, double tau_ip, double* dX, void* stream);
+
+/* Replaces BOLDModel.Sim(rE, nnodes, dt) (call site netwWilsonCowanPlastic.py:144).
+ *   rE [B,T,N] -> bold [B,T,N]; explicit-Euler Balloon-Windkessel, bold[t] from the state before rE[t]. */
+int nrem_bold_sim_f64(const double* rE, int B, int64_t T, int N, double dt, double* bold, void* stream);
+
+/* Replaces the cut + filtfilt + decimate of simBOLD (netwWilsonCowanPlastic.py:145-156).
+ *   bold [B,T,N]; the first Neq rows are dropped; zero-phase IIR (h_b, h_a: 5 coefficients each,
+ *   host pointers, SciPy order, a[0] = 1) with SciPy's default odd padding of 15 and lfilter_zi
+ *   start-up; every ds-th row is kept -> out [B, ceil((T-Neq)/ds), N].
+ *   scratch: device, >= nrem_filt_scratch_bytes(B,T,N,Neq,ds) bytes.                           */
+int64_t nrem_filt_scratch_bytes(int B, int64_t T, int N, int64_t Neq, int64_t ds);
+int nrem_filtfilt_decimate_f64(const double* bold, int B, int64_t T, int N, int64_t Neq, int64_t ds,
+                               const double* h_b, const double* h_a, double* out, void* scratch, void* stream);
+
+/* Replaces np.corrcoef(BOLD.T) (whole_sweep_both.py:81).  bold [B,J,N] -> fc [B,N,N].          */
+int nrem_fc_f64(const double* bold, int B, int64_t J, int N, double* fc, void* stream);
+
+/* Replaces utils.get_all_metrics(sFC, empFC, data_range=1) for K targets (utils.py:42-50,
+ * whole_sweep_both.py:83-86) and sFC.mean() (whole_sweep_both.py:94).
+ *   fc [B,N,N], emp [K,N,N] -> gof [B,K,4] = (corr, euc, ssim, new_metric); meanfc [B] (may be NULL). */
+int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, double data_range,
+                 double* gof, double* meanfc, void* stream);
+
+/* ---- fused sweep (the fast path; no counterpart in the reference) ------------------------- */
+
+/* Per-simulation parameters of a G x sigma x seed x map sweep
+ * (whole_sweep_both.py:68-72, whole_sweep_both_maps.py:104-108, run_many_seeds.py:115-119):
+ *     G_i     = G0[b]     + dG[b]     * mapG[map_id[b]][i]
+ *     sigma_i = sigma0[b] + dsigma[b] * mapS[map_id[b]][i]
+ * Simulations are processed in tiles of NREM_TILE_SIMS; all simulations of one tile must share
+ * map_id (the host layer pads).                                                               */
+#define NREM_TILE_SIMS 128
+
+typedef struct nrem_sweep_plan nrem_sweep_plan;   /* opaque; owns device scratch */
+
+typedef struct nrem_sweep_opts {
+    int32_t kernel;          /* 0 = auto, 1 = CUDA-core coupling, 2 = tcgen05 (TF32) coupling, 3 = tcgen05 3xTF32 */
+    int32_t bold_f32;        /* 1 = Balloon-Windkessel state in float32 (default 0 = float64)      */
+    int32_t chunk_samples;   /* stored samples per launch of the integrator (0 = default)           */
+    int32_t want_fc;         /* 1 = also return the FC matrices                                      */
+    int64_t Neq;             /* rows dropped before filtering (reference: 2000)                      */
+    int64_t bold_downsamp;   /* decimation after filtering (reference: 1000)                         */
+    double  bold_dt;         /* BOLD Euler step (reference: dt*downsamp = 0.04)                      */
+    double  b[5], a[5];      /* band-pass coefficients, SciPy order                                  */
+} nrem_sweep_opts;
+
+int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, int n_maps, int K,
+                      nrem_sweep_plan** plan);
+int nrem_sweep_destroy(nrem_sweep_plan* plan);
+int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan);
+
+/* Runs the whole pipeline for B simulations.
+ *   CM [N,N] f64; mapG,mapS [n_maps,N] f64; G0,dG,sigma0,dsigma [B] f64; h_map_id [B] i32 (HOST pointer, may be NULL = all 0);
+ *   streams [B] u64; emp [K,N,N] f64
+ *   gof [B,K,4] f64; extra [B,4] f64 = (mean FC, 0, 0, 0) (reserved for sync/meta/peakfreq);
+ *   fc NULL or [B,N,N] f64.
+ * Returns after the last kernel has been enqueued on `stream`.                                 */
+int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,
+                   const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                   const int32_t* h_map_id, const uint64_t* streams, const double* emp,
+                   double* gof, double* extra, double* fc, void* stream);
+
+/* Test hooks for the sweep's integrator: advance B simulations n1+n2+n3 steps with kernel
+ * variant `kernel` and return the float32 E samples [nrec, N, Bpad] (Bpad = B rounded up to
+ * NREM_TILE_SIMS, simulation fastest) and the final state [3, N, Bpad].                        */
+int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG,
+                             const double* mapS, const double* G0, const double* dG, const double* sigma0,
+                             const double* dsigma, const int32_t* h_map_id, const uint64_t* streams, int B,
+                             int n_maps, int64_t nrec, float* E_samples, float* final_state, void* stream);
+
+/* Kernel launches issued by this library on the calling thread since the last reset. */
+int64_t nrem_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NREMFC_H */

@@ -1,0 +1,175 @@
+// FC = Pearson correlation over time, and goodness of fit against K empirical matrices.
+//
+// Replaces np.corrcoef(BOLD.T) (whole_sweep_both.py:81), utils.get_all_metrics
+// (utils.py:42-50, incl. new_metric utils.py:28-31 and scikit-image's structural_similarity
+// at its defaults, call site utils.py:48) and sFC.mean() (whole_sweep_both.py:94).
+// One CTA per simulation; all reductions are warp-shuffle + one shared-memory hop, float64.
+#pragma once
+#include "common.cuh"
+
+namespace nrem {
+
+constexpr int kFcThreads = 512;
+constexpr int kFcMaxPairs = 17;     // ceil(N(N+1)/2 / 512) for N <= 128
+constexpr int kFcTile = 32;         // time rows per shared-memory tile
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the CTA; result valid in every thread.  red: >= 33 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// bold [B][J][N] -> fc [B][N][N].   dynamic smem: (2*N + kFcTile*N) doubles
+__global__ void __launch_bounds__(kFcThreads) fc_f64_kernel(const double* bold, int64_t J, int N, double* fc) {
+    extern __shared__ double smf[];
+    double* mean = smf;
+    double* sd = smf + N;
+    double* tile = smf + 2 * N;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const double* x = bold + (size_t)b * J * N;
+    if (tid < N) {
+        double m = 0.0;
+        for (int64_t t = 0; t < J; ++t) m += x[t * N + tid];
+        mean[tid] = m / (double)J;
+    }
+    const int npairs = N * (N + 1) / 2;
+    int pi[kFcMaxPairs], pj[kFcMaxPairs];
+    double acc[kFcMaxPairs];
+#pragma unroll
+    for (int q = 0; q < kFcMaxPairs; ++q) {
+        acc[q] = 0.0;
+        int p = tid + q * kFcThreads;
+        int i = 0;
+        if (p < npairs) {
+            // row-major upper triangle incl. diagonal: row i holds N - i entries
+            int rem = p;
+            while (rem >= N - i) { rem -= N - i; ++i; }
+            pi[q] = i; pj[q] = i + rem;
+        } else {
+            pi[q] = -1; pj[q] = 0;
+        }
+    }
+    __syncthreads();
+    for (int64_t t0 = 0; t0 < J; t0 += kFcTile) {
+        const int rows = (int)min((int64_t)kFcTile, J - t0);
+        for (int k = tid; k < rows * N; k += kFcThreads) tile[k] = x[t0 * N + k] - mean[k % N];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kFcMaxPairs; ++q) {
+            if (pi[q] >= 0) {
+                double a = acc[q];
+                for (int r = 0; r < rows; ++r) a = fma(tile[r * N + pi[q]], tile[r * N + pj[q]], a);
+                acc[q] = a;
+            }
+        }
+        __syncthreads();
+    }
+    const double inv = 1.0 / (double)(J - 1);              // np.cov: c *= 1/(J-1)
+#pragma unroll
+    for (int q = 0; q < kFcMaxPairs; ++q) {
+        acc[q] *= inv;
+        if (pi[q] >= 0 && pi[q] == pj[q]) sd[pi[q]] = sqrt(acc[q]);
+    }
+    __syncthreads();
+    double* o = fc + (size_t)b * N * N;
+#pragma unroll
+    for (int q = 0; q < kFcMaxPairs; ++q) {
+        if (pi[q] >= 0) {
+            double c = acc[q] / sd[pi[q]];                 // np.corrcoef: c /= stddev[:,None]; c /= stddev[None,:]
+            c = c / sd[pj[q]];
+            c = fmin(1.0, fmax(-1.0, c));                  // np.clip(c.real, -1, 1)
+            o[pi[q] * N + pj[q]] = c;
+            o[pj[q] * N + pi[q]] = c;
+        }
+    }
+}
+
+// fc [B][N][N], emp [K][N][N] -> gof [B][K][4] = (corr, euc, ssim, new_metric), meanfc [B].
+// dynamic smem: (2*N*N + 40) doubles
+__global__ void __launch_bounds__(256) gof_f64_kernel(const double* fc, const double* emp, int K, int N, double data_range,
+                                                      double* gof, double* meanfc) {
+    extern __shared__ double smg[];
+    double* S = smg;
+    double* Em = smg + N * N;
+    double* red = smg + 2 * N * N;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int NN = N * N;
+    for (int k = tid; k < NN; k += nt) S[k] = fc[(size_t)b * NN + k];
+    __syncthreads();
+    {
+        double s = 0.0;
+        for (int k = tid; k < NN; k += nt) s += S[k];
+        s = block_sum(s, red);
+        if (tid == 0 && meanfc) meanfc[b] = s / (double)NN;
+    }
+    const double P = 0.5 * (double)N * (double)(N - 1);
+    const int W = N - 6;                                      // 7x7 windows fully inside: (N-6)^2
+    const double C1 = (0.01 * data_range) * (0.01 * data_range), C2 = (0.03 * data_range) * (0.03 * data_range);
+    const double cov_norm = 49.0 / 48.0;                      // sample covariance (use_sample_covariance=True)
+    for (int kt = 0; kt < K; ++kt) {
+        __syncthreads();
+        for (int k = tid; k < NN; k += nt) Em[k] = emp[(size_t)kt * NN + k];
+        __syncthreads();
+        // strict upper triangle, two-pass Pearson (np.corrcoef of the two flattened vectors)
+        double ss = 0.0, se = 0.0;
+        for (int k = tid; k < NN; k += nt) {
+            const int i = k / N, j = k % N;
+            if (j > i) { ss += S[k]; se += Em[k]; }
+        }
+        const double ms = block_sum(ss, red) / P;
+        const double me = block_sum(se, red) / P;
+        double css = 0.0, cee = 0.0, cse = 0.0, d2 = 0.0;
+        for (int k = tid; k < NN; k += nt) {
+            const int i = k / N, j = k % N;
+            if (j > i) {
+                const double a = S[k] - ms, c = Em[k] - me, d = Em[k] - S[k];
+                css = fma(a, a, css); cee = fma(c, c, cee); cse = fma(a, c, cse); d2 = fma(d, d, d2);
+            }
+        }
+        css = block_sum(css, red); cee = block_sum(cee, red); cse = block_sum(cse, red); d2 = block_sum(d2, red);
+        // SSIM, uniform 7x7 window, mean over the (N-6)^2 interior positions
+        double sacc = 0.0;
+        for (int wdx = tid; wdx < W * W; wdx += nt) {
+            const int r0 = wdx / W, c0 = wdx % W;
+            double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+            for (int r = 0; r < 7; ++r) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c) {
+                    const double xv = S[(r0 + r) * N + c0 + c], yv = Em[(r0 + r) * N + c0 + c];
+                    sx += xv; sy += yv;
+                    sxx = fma(xv, xv, sxx); syy = fma(yv, yv, syy); sxy = fma(xv, yv, sxy);
+                }
+            }
+            const double ux = sx / 49.0, uy = sy / 49.0, uxx = sxx / 49.0, uyy = syy / 49.0, uxy = sxy / 49.0;
+            const double vx = cov_norm * (uxx - ux * ux), vy = cov_norm * (uyy - uy * uy), vxy = cov_norm * (uxy - ux * uy);
+            sacc += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+        }
+        sacc = block_sum(sacc, red);
+        if (tid == 0) {
+            const double corr = (cse / (P - 1)) / sqrt(css / (P - 1)) / sqrt(cee / (P - 1));
+            double* o = gof + ((size_t)b * K + kt) * 4;
+            o[0] = corr;
+            o[1] = sqrt(d2);
+            o[2] = sacc / (double)(W * W);
+            o[3] = (1.0 - corr) + (ms - me) * (ms - me);
+        }
+    }
+}
+
+}  // namespace nrem

@@ -1,0 +1,490 @@
+// C ABI of libnremfc (see include/nremfc.h).  Host-side orchestration only: argument checks,
+// filter-coefficient preparation, scratch carving and kernel launches.  No CPU compute fallback.
+#include <algorithm>
+#include <complex>
+#include <new>
+#include <vector>
+
+#include "bold_filter.cuh"
+#include "common.cuh"
+#include "fc_gof.cuh"
+#include "wc_batch.cuh"
+#include "wc_f64.cuh"
+#include "wc_tc.cuh"
+
+namespace nrem {
+thread_local char g_err[512] = "";
+thread_local int64_t g_launches = 0;
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// ---- zero-phase filter preparation ---------------------------------------------------------------
+struct FiltHost {
+    FiltCoef f;
+    std::vector<double> ptab;     // [(ds + 2*kPad)][4]
+};
+
+// H(z) = B(z)/A(z), order 4 with two complex-conjugate pole pairs -> parallel form (see bold_filter.cuh)
+static int prepare_filter(const double* hb, const double* ha, int64_t Tf, int64_t ds, FiltHost& out) {
+    typedef long double LD;
+    typedef std::complex<LD> C;
+    if (ha[0] != 1.0) return fail(NREM_ERR_ARG, "filter: a[0] must be 1%s%s");
+    LD a[5], b[5];
+    for (int i = 0; i < 5; ++i) { a[i] = ha[i]; b[i] = hb[i]; }
+    // Durand-Kerner on z^4 + a1 z^3 + a2 z^2 + a3 z + a4
+    C r[4] = {C(0.4L, 0.9L), C(-0.65L, 0.72L), C(0.97L, -0.06L), C(0.3L, -0.8L)};
+    auto poly = [&](C z) { return (((z + a[1]) * z + a[2]) * z + a[3]) * z + a[4]; };
+    for (int it = 0; it < 500; ++it) {
+        for (int i = 0; i < 4; ++i) {
+            C d = 1;
+            for (int j = 0; j < 4; ++j) if (j != i) d *= (r[i] - r[j]);
+            r[i] -= poly(r[i]) / d;
+        }
+    }
+    for (int it = 0; it < 4; ++it)       // Newton polish
+        for (int i = 0; i < 4; ++i) {
+            C z = r[i];
+            C dp = ((4.0L * z + 3.0L * a[1]) * z + 2.0L * a[2]) * z + a[3];
+            r[i] -= poly(z) / dp;
+        }
+    C p[2];
+    int np = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (std::abs(r[i]) >= 1.0L) return fail(NREM_ERR_ARG, "filter: unstable pole%s%s");
+        if (r[i].imag() > 1e-12L) { if (np < 2) p[np] = r[i]; ++np; }
+    }
+    if (np != 2) return fail(NREM_ERR_UNSUPPORTED, "filter: need two complex-conjugate pole pairs%s%s");
+    // residues of the strictly proper part
+    LD nr[4];
+    for (int i = 0; i < 4; ++i) nr[i] = b[i + 1] - b[0] * a[i + 1];
+    FiltCoef& f = out.f;
+    f.b0 = (double)b[0];
+    const int64_t J = (Tf + ds - 1) / ds, M = Tf + 2 * kPad;
+    const int64_t Llast = M - 16 - (J - 1) * ds;
+    for (int q = 0; q < 2; ++q) {
+        C z = p[q];
+        C num = ((nr[0] * z + nr[1]) * z + nr[2]) * z + nr[3];
+        C den = 1;
+        for (int i = 0; i < 4; ++i) if (std::abs(r[i] - z) > 1e-15L) den *= (z - r[i]);
+        C rho = num / den;
+        C Q = C(1) / (C(1) - z);
+        C PL = std::pow(z, (LD)ds), PE = std::pow(z, (LD)Llast);
+        f.Pr[q] = (double)z.real(); f.Pi[q] = (double)z.imag();
+        f.Rr[q] = (double)rho.real(); f.Ri[q] = (double)rho.imag();
+        f.Qr[q] = (double)Q.real(); f.Qi[q] = (double)Q.imag();
+        f.PLr[q] = (double)PL.real(); f.PLi[q] = (double)PL.imag();
+        f.PEr[q] = (double)PE.real(); f.PEi[q] = (double)PE.imag();
+    }
+    f.Tf = Tf; f.ds = ds; f.J = J; f.M = M; f.ptab = nullptr;
+    const int64_t K = ds + 2 * kPad;
+    out.ptab.resize((size_t)K * 4);
+    C pw[2] = {C(1), C(1)};
+    for (int64_t k = 0; k < K; ++k) {
+        for (int q = 0; q < 2; ++q) {
+            out.ptab[(size_t)k * 4 + 2 * q] = (double)pw[q].real();
+            out.ptab[(size_t)k * 4 + 2 * q + 1] = (double)pw[q].imag();
+            pw[q] *= p[q];
+        }
+    }
+    return NREM_OK;
+}
+
+static int64_t filt_scratch_doubles(int64_t nth, int64_t J, int64_t ds) {
+    // fs 4, cs 4, head 16, tail 16, summ 4J, wdec J, wlast 1  (per slot) + ptab
+    return nth * (4 + 4 + 16 + 16 + 5 * J + 1) + (ds + 2 * kPad) * 4;
+}
+
+static FiltScratch carve_filt(double* base, int64_t nth, int64_t J, double** ptab_dev) {
+    FiltScratch S;
+    S.nth = nth;
+    double* p = base;
+    S.fs = p; p += 4 * nth;
+    S.cs = p; p += 4 * nth;
+    S.head = p; p += 16 * nth;
+    S.tail = p; p += 16 * nth;
+    S.summ = p; p += 4 * J * nth;
+    S.wdec = p; p += J * nth;
+    S.wlast = p; p += nth;
+    *ptab_dev = p;
+    return S;
+}
+
+}  // namespace nrem
+
+using namespace nrem;
+
+extern "C" {
+
+int nrem_abi_version(void) { return NREM_ABI_VERSION; }
+const char* nrem_last_error(void) { return g_err; }
+int nrem_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t nrem_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+static int check_params(const nrem_wc_params* p) {
+    NREM_REQUIRE(p != nullptr, "params is null");
+    NREM_REQUIRE(p->nnodes >= 1, "nnodes must be positive");
+    NREM_REQUIRE(p->n1 >= 0 && p->n2 >= 0 && p->n3 >= 0, "phase lengths must be non-negative");
+    NREM_REQUIRE(p->n1 + p->n2 + p->n3 < (int64_t)0xFFFFFFFFll, "more than 2^32-1 Euler steps");
+    NREM_REQUIRE(p->downsamp >= 1, "downsamp must be >= 1");
+    NREM_REQUIRE(p->tauE > 0 && p->tauI > 0 && p->tau_ip[0] > 0 && p->tau_ip[1] > 0 && p->tau_ip[2] > 0, "time constants must be positive");
+    return NREM_OK;
+}
+
+int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, const double* sigmaE,
+                    const uint64_t* streams, const double* noise, int noise_batch, int B, int64_t nrec,
+                    double* Y, double* final_state, void* stream) {
+    if (int rc = check_params(p)) return rc;
+    NREM_REQUIRE(CM && G && sigmaE, "CM, G and sigmaE are required");
+    NREM_REQUIRE(B >= 1, "B must be positive");
+    NREM_REQUIRE(p->nnodes <= 1024, "nnodes > 1024 is not supported by the float64 path");
+    NREM_REQUIRE(!noise || noise_batch == 1 || noise_batch == B, "noise_batch must be 1 or B");
+    NREM_REQUIRE(!Y || nrec >= 1, "nrec must be positive when Y is given");
+    WcF64Args A;
+    A.p = *p; A.CM = CM; A.G = G; A.sg = sigmaE; A.streams = streams; A.noise = noise;
+    A.noise_batch = noise ? noise_batch : 1; A.nrec = nrec; A.Y = Y; A.fin = final_state;
+    const int N = p->nnodes;
+    const int threads = (int)round_up(N, 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sm_small = sizeof(double) * 2 * N, sm_big = sm_small + sizeof(double) * (size_t)N * N;
+    if (sm_big <= 200 * 1024) {
+        NREM_CUDA(cudaFuncSetAttribute(wc_run_f64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big));
+        wc_run_f64_kernel<true><<<B, threads, sm_big, st>>>(A);
+    } else {
+        wc_run_f64_kernel<false><<<B, threads, sm_small, st>>>(A);
+    }
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+int nrem_wc_derivative_f64(const nrem_wc_params* p, const double* CM, const double* X, const double* G,
+                           const double* sigmaE, const double* noise, double tau_ip, double* dX, void* stream) {
+    if (int rc = check_params(p)) return rc;
+    NREM_REQUIRE(CM && X && G && sigmaE && dX, "null array");
+    NREM_REQUIRE(tau_ip > 0, "tau_ip must be positive");
+    const int N = p->nnodes;
+    wc_derivative_f64_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*p, CM, X, G, sigmaE, noise, tau_ip, dX);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+int nrem_bold_sim_f64(const double* rE, int B, int64_t T, int N, double dt, double* bold, void* stream) {
+    NREM_REQUIRE(rE && bold, "null array");
+    NREM_REQUIRE(B >= 1 && T >= 1 && N >= 1, "bad shape");
+    const int64_t n = (int64_t)B * N;
+    bold_sim_f64_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(rE, B, T, N, dt, bold);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+int64_t nrem_filt_scratch_bytes(int B, int64_t T, int N, int64_t Neq, int64_t ds) {
+    if (B < 1 || N < 1 || ds < 1 || T - Neq < 32) return -1;
+    const int64_t Tf = T - Neq, J = (Tf + ds - 1) / ds;
+    return 8 * filt_scratch_doubles((int64_t)B * N, J, ds);
+}
+
+int nrem_filtfilt_decimate_f64(const double* bold, int B, int64_t T, int N, int64_t Neq, int64_t ds,
+                               const double* h_b, const double* h_a, double* out, void* scratch, void* stream) {
+    NREM_REQUIRE(bold && out && scratch && h_b && h_a, "null array");
+    NREM_REQUIRE(B >= 1 && N >= 1 && ds >= 1 && Neq >= 0, "bad shape");
+    NREM_REQUIRE(T - Neq >= 32, "need at least 32 samples after the cut");
+    FiltHost fh;
+    const int64_t Tf = T - Neq;
+    if (int rc = prepare_filter(h_b, h_a, Tf, ds, fh)) return rc;
+    const int64_t nth = (int64_t)B * N;
+    double* ptab_dev;
+    FiltScratch S = carve_filt((double*)scratch, nth, fh.f.J, &ptab_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    NREM_CUDA(cudaMemcpyAsync(ptab_dev, fh.ptab.data(), fh.ptab.size() * 8, cudaMemcpyHostToDevice, st));
+    NREM_CUDA(cudaStreamSynchronize(st));       // fh.ptab is pageable host memory owned by this frame
+    fh.f.ptab = ptab_dev;
+    filt_forward_f64_kernel<<<(unsigned)((nth + 63) / 64), 64, 0, st>>>(bold, B, T, N, Neq, fh.f, S);
+    NREM_LAUNCHED();
+    filt_backward_kernel<<<(unsigned)((nth + 63) / 64), 64, 0, st>>>(fh.f, S, nth, N, B, 0, out, fh.f.J * N, N, 1, B);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+int nrem_fc_f64(const double* bold, int B, int64_t J, int N, double* fc, void* stream) {
+    NREM_REQUIRE(bold && fc, "null array");
+    NREM_REQUIRE(B >= 1 && J >= 2, "bad shape");
+    NREM_REQUIRE(N >= 1 && N <= 128, "fc supports 1 <= N <= 128");
+    const size_t sm = sizeof(double) * (2 * N + kFcTile * N);
+    fc_f64_kernel<<<B, kFcThreads, sm, (cudaStream_t)stream>>>(bold, J, N, fc);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, double data_range,
+                 double* gof, double* meanfc, void* stream) {
+    NREM_REQUIRE(fc && emp && gof, "null array");
+    NREM_REQUIRE(B >= 1 && K >= 1, "bad shape");
+    NREM_REQUIRE(N >= 7 && N <= 118, "gof supports 7 <= N <= 118");
+    const size_t sm = sizeof(double) * (2 * (size_t)N * N + 40);
+    NREM_CUDA(cudaFuncSetAttribute(gof_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    gof_f64_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(fc, emp, K, N, data_range, gof, meanfc);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+// ---- fused sweep -------------------------------------------------------------------------------
+
+struct nrem_sweep_plan {
+    nrem_wc_params p;
+    nrem_sweep_opts o;
+    int B, n_maps, K, N;
+    int64_t Bs, tiles, T, Tf, J, nth;
+    int chunk_samples;
+    FiltHost fh;
+    FiltScratch S;
+    // device memory (one allocation)
+    void* dev;
+    int64_t dev_bytes;
+    float *state, *SCp, *mapG, *mapS, *par, *Ebuf;
+    int32_t* tile_map;
+    uint64_t* streams;
+    void* bw_state;
+    double *bold_dec, *fc;
+};
+
+static BatchConst make_const(const nrem_wc_params& p) {
+    BatchConst c;
+    c.a_ee = (float)p.a_ee; c.a_ei = (float)p.a_ei; c.a_ii = (float)p.a_ii; c.P = (float)p.P; c.rhoE = (float)p.rhoE;
+    c.rE = (float)p.rE; c.rI = (float)p.rI; c.mu = (float)p.mu; c.sq = (float)p.sqdtD;
+    c.kE = (float)(p.dtSim / p.tauE); c.kI = (float)(p.dtSim / p.tauI);
+    c.sigI2 = (float)(-p.sigmaI * 1.4426950408889634);
+    c.E0 = (float)p.E0; c.I0 = (float)p.I0; c.a0 = (float)p.a_ie_0;
+    c.k0 = (uint32_t)p.seed; c.k1 = (uint32_t)(p.seed >> 32);
+    c.N = p.nnodes;
+    return c;
+}
+
+static int resolve_kernel(int kernel) {
+    if (kernel == 0) return 1;
+    return kernel;
+}
+
+// Launch one piece of the integrator.
+static int launch_integrator(int kernel, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
+    switch (resolve_kernel(kernel)) {
+        case 1:
+            NREM_CUDA(cudaFuncSetAttribute(wc_batch_v0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV0SmemBytes));
+            wc_batch_v0_kernel<<<(unsigned)tiles, kBatchThreads, kV0SmemBytes, st>>>(A);
+            break;
+        case 2:
+        case 3:
+            return launch_wc_tc(resolve_kernel(kernel), A, tiles, st);
+        default:
+            return fail(NREM_ERR_ARG, "unknown integrator kernel%s%s");
+    }
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+struct StagePtrs {
+    float *state, *SCp, *mapG, *mapS, *par, *Ebuf;
+    int32_t* tile_map;
+    uint64_t* streams;
+};
+
+// Copies/convert the float64 API arrays into the padded float32 device layout.
+static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, const double* CM, const double* mapG,
+                        const double* mapS, const double* G0, const double* dG, const double* s0, const double* ds,
+                        const int32_t* h_map_id, const uint64_t* streams, const StagePtrs& d, cudaStream_t st) {
+    const int N = p.nnodes;
+    std::vector<int32_t> tm((size_t)(Bs / kTile));
+    for (int64_t t = 0; t < Bs / kTile; ++t) {
+        const int64_t first = t * kTile;
+        const int32_t m = h_map_id ? h_map_id[std::min<int64_t>(first, B - 1)] : 0;
+        if (m < 0 || m >= n_maps) return fail(NREM_ERR_ARG, "map_id out of range%s%s");
+        for (int64_t s = first; s < std::min<int64_t>(first + kTile, B); ++s)
+            if (h_map_id && h_map_id[s] != m) return fail(NREM_ERR_ARG, "all simulations of a 128-tile must share map_id%s%s");
+        tm[(size_t)t] = m;
+    }
+    NREM_CUDA(cudaMemcpyAsync(d.tile_map, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice, st));
+    NREM_CUDA(cudaStreamSynchronize(st));
+    stage_sc_kernel<<<(kNPad * kNPad + 255) / 256, 256, 0, st>>>(CM, N, d.SCp);
+    NREM_LAUNCHED();
+    stage_maps_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(mapG, mapS, n_maps, N, d.mapG, d.mapS);
+    NREM_LAUNCHED();
+    stage_par_kernel<<<(unsigned)((Bs + 255) / 256), 256, 0, st>>>(G0, dG, s0, ds, streams, B, Bs, d.par, d.streams);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, int n_maps, int K, nrem_sweep_plan** plan) {
+    if (int rc = check_params(p)) return rc;
+    NREM_REQUIRE(o && plan, "null argument");
+    NREM_REQUIRE(B >= 1 && n_maps >= 1 && K >= 1, "bad shape");
+    NREM_REQUIRE(p->nnodes >= 7 && p->nnodes <= kNPad, "the sweep supports 7 <= nnodes <= 96");
+    NREM_REQUIRE(o->bold_downsamp >= 1 && o->Neq >= 0, "bad BOLD options");
+    nrem_sweep_plan* P = new (std::nothrow) nrem_sweep_plan();
+    if (!P) return fail(NREM_ERR_ARG, "out of host memory%s%s");
+    P->p = *p; P->o = *o; P->B = B; P->n_maps = n_maps; P->K = K; P->N = p->nnodes; P->dev = nullptr;
+    P->Bs = round_up(B, kTile); P->tiles = P->Bs / kTile;
+    P->T = (p->n3 + p->downsamp - 1) / p->downsamp;
+    P->Tf = P->T - o->Neq;
+    if (P->Tf < 32) { delete P; return fail(NREM_ERR_ARG, "fewer than 32 BOLD samples after the Neq cut%s%s"); }
+    P->J = (P->Tf + o->bold_downsamp - 1) / o->bold_downsamp;
+    P->nth = (int64_t)P->N * P->Bs;
+    P->chunk_samples = o->chunk_samples > 0 ? o->chunk_samples : 250;
+    if (int rc = prepare_filter(o->b, o->a, P->Tf, o->bold_downsamp, P->fh)) { delete P; return rc; }
+    // carve one device allocation
+    const int N = P->N;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
+    const int64_t o_state = take(4 * 3 * (int64_t)N * P->Bs);
+    const int64_t o_sc = take(4 * kNPad * kNPad);
+    const int64_t o_mg = take(4 * (int64_t)n_maps * kNPad);
+    const int64_t o_ms = take(4 * (int64_t)n_maps * kNPad);
+    const int64_t o_par = take(4 * 4 * P->Bs);
+    const int64_t o_tm = take(4 * P->tiles);
+    const int64_t o_st = take(8 * P->Bs);
+    const int64_t o_eb = take(4 * (int64_t)P->chunk_samples * N * P->Bs);
+    const int64_t o_bw = take((o->bold_f32 ? 4 : 8) * 4 * P->nth);
+    const int64_t o_fs = take(8 * filt_scratch_doubles(P->nth, P->J, o->bold_downsamp));
+    const int64_t o_bd = take(8 * (int64_t)B * P->J * N);
+    const int64_t o_fc = take(8 * (int64_t)B * N * N);
+    P->dev_bytes = off;
+    cudaError_t e = cudaMalloc(&P->dev, (size_t)off);
+    if (e != cudaSuccess) { delete P; return fail(NREM_ERR_CUDA, "cudaMalloc(sweep plan): %s%s", cudaGetErrorString(e)); }
+    char* base = (char*)P->dev;
+    P->state = (float*)(base + o_state); P->SCp = (float*)(base + o_sc); P->mapG = (float*)(base + o_mg);
+    P->mapS = (float*)(base + o_ms); P->par = (float*)(base + o_par); P->tile_map = (int32_t*)(base + o_tm);
+    P->streams = (uint64_t*)(base + o_st); P->Ebuf = (float*)(base + o_eb); P->bw_state = base + o_bw;
+    double* ptab_dev;
+    P->S = carve_filt((double*)(base + o_fs), P->nth, P->J, &ptab_dev);
+    P->fh.f.ptab = ptab_dev;
+    P->bold_dec = (double*)(base + o_bd); P->fc = (double*)(base + o_fc);
+    e = cudaMemcpy(ptab_dev, P->fh.ptab.data(), P->fh.ptab.size() * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(P->dev); delete P; return fail(NREM_ERR_CUDA, "cudaMemcpy(ptab): %s%s", cudaGetErrorString(e)); }
+    *plan = P;
+    return NREM_OK;
+}
+
+int nrem_sweep_destroy(nrem_sweep_plan* plan) {
+    if (!plan) return NREM_OK;
+    if (plan->dev) cudaFree(plan->dev);
+    delete plan;
+    return NREM_OK;
+}
+
+int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan) { return plan ? plan->dev_bytes : -1; }
+
+// Runs phases 1-3; when Ebuf_all != NULL every sample goes to it (test hook), otherwise the
+// samples of each chunk are consumed by the BOLD/filter kernel of the plan.
+static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, int64_t Bs, int chunk_samples,
+                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st) {
+    BatchArgs A;
+    A.c = make_const(p);
+    A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
+    A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp;
+    const int64_t tiles = Bs / kTile;
+    const int64_t ns[3] = {p.n1, p.n2, p.n3};
+    const int64_t chunk_steps = (int64_t)chunk_samples * p.downsamp;
+    int64_t step = 0;
+    bool first = true;
+    for (int ph = 0; ph < 3; ++ph) {
+        A.kA = (float)(p.dtSim / p.tau_ip[ph]);
+        for (int64_t i0 = 0; i0 < ns[ph]; i0 += chunk_steps) {
+            const int64_t n = std::min(chunk_steps, ns[ph] - i0);
+            A.step0 = (uint32_t)step; A.nsteps = (int)n; A.init = first ? 1 : 0;
+            A.rec = (ph == 2); A.rec_phase = 0;        // chunks start on a multiple of downsamp
+            const int64_t row_base = i0 / p.downsamp;
+            const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
+            if (Ebuf_all) { A.Ebuf = Ebuf_all; A.row0 = row_base; }
+            else { A.Ebuf = d.Ebuf; A.row0 = 0; }
+            if (int rc = launch_integrator(kernel, A, tiles, st)) return rc;
+            if (ph == 2 && plan) {
+                const int64_t nth = plan->nth;
+                const unsigned blocks = (unsigned)((nth + 127) / 128);
+                if (plan->o.bold_f32)
+                    bold_filter_chunk_kernel<float><<<blocks, 128, 0, st>>>(d.Ebuf, rows, row_base, plan->N, Bs, plan->o.Neq,
+                                                                         (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S);
+                else
+                    bold_filter_chunk_kernel<double><<<blocks, 128, 0, st>>>(d.Ebuf, rows, row_base, plan->N, Bs, plan->o.Neq,
+                                                                          plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S);
+                NREM_LAUNCHED();
+            }
+            step += n;
+            first = false;
+        }
+    }
+    return NREM_OK;
+}
+
+int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, const double* mapS,
+                   const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                   const int32_t* h_map_id, const uint64_t* streams, const double* emp,
+                   double* gof, double* extra, double* fc, void* stream) {
+    NREM_REQUIRE(P, "plan is null");
+    NREM_REQUIRE(CM && mapG && mapS && G0 && dG && sigma0 && dsigma && streams && emp && gof, "null array");
+    cudaStream_t st = (cudaStream_t)stream;
+    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
+    if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st)) return rc;
+    if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st)) return rc;
+    const int N = P->N;
+    filt_backward_kernel<<<(unsigned)((P->nth + 127) / 128), 128, 0, st>>>(P->fh.f, P->S, P->nth, N, P->Bs, 1, P->bold_dec,
+                                                                         P->J * N, N, 1, P->B);
+    NREM_LAUNCHED();
+    double* fcd = fc ? fc : P->fc;
+    if (int rc = nrem_fc_f64(P->bold_dec, P->B, P->J, N, fcd, stream)) return rc;
+    double* meanfc = nullptr;
+    if (extra) {
+        NREM_CUDA(cudaMemsetAsync(extra, 0, sizeof(double) * 4 * P->B, st));
+        // mean FC goes to extra[b][0]: computed into the plan's scratch then scattered
+        meanfc = P->bold_dec;           // bold_dec is dead after nrem_fc_f64; reuse its first B doubles
+    }
+    if (int rc = nrem_gof_f64(fcd, emp, P->B, P->K, N, 1.0, gof, meanfc, stream)) return rc;
+    if (extra) {
+        NREM_CUDA(cudaMemcpy2DAsync(extra, 4 * sizeof(double), meanfc, sizeof(double), sizeof(double), P->B,
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    return NREM_OK;
+}
+
+int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG,
+                             const double* mapS, const double* G0, const double* dG, const double* sigma0,
+                             const double* dsigma, const int32_t* h_map_id, const uint64_t* streams, int B,
+                             int n_maps, int64_t nrec, float* E_samples, float* final_state, void* stream) {
+    if (int rc = check_params(p)) return rc;
+    NREM_REQUIRE(CM && mapG && mapS && G0 && dG && sigma0 && dsigma && streams, "null array");
+    NREM_REQUIRE(B >= 1 && n_maps >= 1, "bad shape");
+    NREM_REQUIRE(p->nnodes >= 1 && p->nnodes <= kNPad, "the sweep supports nnodes <= 96");
+    NREM_REQUIRE(!E_samples || nrec >= (p->n3 + p->downsamp - 1) / p->downsamp, "nrec too small");
+    NREM_REQUIRE(final_state, "final_state is required");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = p->nnodes;
+    const int64_t Bs = round_up(B, kTile);
+    // scratch: everything except the state (which is the caller's final_state buffer)
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
+    const int64_t o_sc = take(4 * kNPad * kNPad), o_mg = take(4 * (int64_t)n_maps * kNPad), o_ms = take(4 * (int64_t)n_maps * kNPad);
+    const int64_t o_par = take(4 * 4 * Bs), o_tm = take(4 * (Bs / kTile)), o_st = take(8 * Bs);
+    const int kDummyRows = 64;
+    const int64_t o_dummy = take(E_samples ? 256 : 4 * (int64_t)kDummyRows * N * Bs);
+    void* dev = nullptr;
+    NREM_CUDA(cudaMalloc(&dev, (size_t)off));
+    char* base = (char*)dev;
+    StagePtrs d{final_state, (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
+                (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
+    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st);
+    if (rc == NREM_OK) {
+        if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st);
+        else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st);   // samples go to a scratch ring
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(NREM_ERR_CUDA, "integrate: %s%s", cudaGetErrorString(e));
+    return NREM_OK;
+}
+
+}  // extern "C"

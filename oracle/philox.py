@@ -18,8 +18,9 @@ counter  = (step, quad, stream & 0xffffffff, stream >> 32)
            stream : per-simulation 64-bit replicate id
 outputs  = x0..x3 (uint32)
 u(x)     = ((x >> 9) + 0.5) * 2**-23                       in (0,1), exact in fp32
-normals  : r0 = sqrt(-2 ln u(x0)); z[4q+0] = r0 cos(2 pi u(x1)); z[4q+1] = r0 sin(2 pi u(x1))
-           r1 = sqrt(-2 ln u(x2)); z[4q+2] = r1 cos(2 pi u(x3)); z[4q+3] = r1 sin(2 pi u(x3))
+theta(x) = 2 pi (u(x) - 0.5)                             in (-pi, pi): the accurate range of MUFU.SIN/COS
+normals  : r0 = sqrt(-2 ln u(x0)); z[4q+0] = r0 cos(theta(x1)); z[4q+1] = r0 sin(theta(x1))
+           r1 = sqrt(-2 ln u(x2)); z[4q+2] = r1 cos(theta(x3)); z[4q+3] = r1 sin(theta(x3))
 noise    = sqdtD * z     (reference: np.random.normal(0, sqdtD, size=N),
                           netwWilsonCowanPlastic.py:80)
 """
@@ -69,7 +70,7 @@ def normals(seed, stream, step, nnodes):
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     r0 = np.sqrt(-2.0 * np.log(uniform23(x0)))
     r1 = np.sqrt(-2.0 * np.log(uniform23(x2)))
-    a0 = 2.0 * np.pi * uniform23(x1)
-    a1 = 2.0 * np.pi * uniform23(x3)
+    a0 = 2.0 * np.pi * (uniform23(x1) - 0.5)
+    a1 = 2.0 * np.pi * (uniform23(x3) - 0.5)
     z = np.stack([r0 * np.cos(a0), r0 * np.sin(a0), r1 * np.cos(a1), r1 * np.sin(a1)], axis=-1)
     return z.reshape(z.shape[:-2] + (nq * 4,))[..., :nnodes]

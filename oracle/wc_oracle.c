@@ -61,8 +61,8 @@ void orc_philox_normals(uint64_t seed, uint64_t stream, uint32_t step, int N, do
         uint32_t x[4];
         double v[4];
         orc_philox4x32_10(ctr, key, x);
-        double r0 = sqrt(-2.0 * log(u23(x[0]))), a0 = two_pi * u23(x[1]);
-        double r1 = sqrt(-2.0 * log(u23(x[2]))), a1 = two_pi * u23(x[3]);
+        double r0 = sqrt(-2.0 * log(u23(x[0]))), a0 = two_pi * (u23(x[1]) - 0.5);
+        double r1 = sqrt(-2.0 * log(u23(x[2]))), a1 = two_pi * (u23(x[3]) - 0.5);
         v[0] = r0 * cos(a0); v[1] = r0 * sin(a0);
         v[2] = r1 * cos(a1); v[3] = r1 * sin(a1);
         for (int j = 0; j < 4 && 4 * q + j < N; ++j) z[4 * q + j] = v[j];

@@ -1,0 +1,259 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (north_star): trajectories within 1e-6 relative and FC within 1e-4 absolute of the
+reference's float64 path when the reference's own noise stream is injected.  The network is
+chaotic (one e-fold per ~1.5 s), so trajectory parity is only definable over a
+short horizon (<= 20 s of simulated time here); full-length parity is statistical
+(test_gpu_statistics.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _noise(seed, steps, N=90):
+    return np.random.RandomState(int(seed)).normal(0, 0.2, size=(steps, N))
+
+
+@pytest.fixture(scope="module")
+def wcmod(aal90):
+    """The drop-in module configured the way whole_sweep_both.py:39-41 does."""
+    import nremmodfc_b200.netwWilsonCowanPlastic as wc
+    wc.P = 0.4
+    wc.rhoE = 0.18
+    wc.CM = aal90["SC"]
+    return wc
+
+
+def _set_times(wc, t1, t2, tstop):
+    wc.tTrans1, wc.tTrans2, wc.tstop = t1, t2, tstop             # whole_sweep_both.py:43-50
+    wc.timeTrans1 = np.arange(0, t1, wc.dtSim)
+    wc.timeTrans2 = np.arange(0, t2, wc.dtSim)
+    wc.timeSim = np.arange(0, tstop, wc.dtSim)
+    wc.time = np.arange(0, tstop, wc.dt)
+
+
+@pytest.mark.parametrize("case", ["homo", "map"])
+def test_run_matches_reference_trajectory(case, wcmod):
+    wc = wcmod
+    g = load_golden(f"wc_short_{case}.npz")
+    _set_times(wc, 0.05, 0.45, 1.0)
+    n1, n2, n3, nrec = [int(v) for v in g["n"]]
+    assert (len(wc.timeTrans1), len(wc.timeTrans2), len(wc.timeSim), len(wc.time)) == (n1, n2, n3, nrec)
+    wc.G = g["G"] if g["G"].ndim else float(g["G"])
+    wc.sigmaE = g["sigmaE"] if g["sigmaE"].ndim else float(g["sigmaE"])
+    wc.noise = _noise(g["seed"], n1 + n2 + n3)
+    wc.run.recompile()
+    Y = wc.run()
+    wc.noise = None
+    assert Y.shape == (nrec, 3, 90) and Y.dtype == np.float64 and Y.flags["C_CONTIGUOUS"]
+    ref = g["Y"]
+    assert np.max(np.abs(Y[g["rows"]] - ref) / np.abs(ref)) < 1e-6          # north_star: 1e-6 relative
+
+
+def test_chain_matches_reference(wcmod, aal90):
+    """run() -> simBOLD() -> corrcoef -> get_all_metrics on the reference's 1+2+17 s golden chain."""
+    from nremmodfc_b200 import ops, utils
+    wc = wcmod
+    g = load_golden("chain_homo.npz")
+    n1, n2, n3, nrec = [int(v) for v in g["n"]]
+    _set_times(wc, 1, 2, 17)
+    wc.G, wc.sigmaE = float(g["G"]), float(g["sigmaE"])
+    wc.noise = _noise(g["seed"], n1 + n2 + n3)
+    wc.run.recompile()
+    tray = wc.run()
+    wc.noise = None
+    E_t = tray[:, 0, :]
+    assert np.max(np.abs(E_t[::100] - g["E_rows"]) / np.abs(g["E_rows"])) < 1e-6
+    assert np.max(np.abs(tray[-1] - g["final"]) / np.abs(g["final"])) < 1e-6
+    BOLD = wc.simBOLD(E_t, nnodes=90, BOLD_downsamp=int(g["BOLD_downsamp"]))
+    assert BOLD.shape == g["BOLD"].shape
+    assert np.max(np.abs(BOLD - g["BOLD"])) < 1e-6 * np.max(np.abs(g["BOLD"]))
+    sFC = ops.fc(BOLD)
+    assert np.max(np.abs(sFC - g["FC"])) < 1e-4                               # north_star: FC 1e-4 absolute
+    assert np.max(np.abs(sFC - g["FC"])) < 1e-6                               # what we actually achieve
+    for k, s in enumerate(("W", "N1", "N2", "N3")):
+        m = utils.get_all_metrics(sFC, aal90[s], data_range=1)
+        assert np.allclose(m, g["gof"][k], atol=1e-6)
+
+
+def test_wc_f64_philox_matches_oracle(aal90, oracle_lib):
+    from nremmodfc_b200 import ops
+    from oracle import wc_oracle
+    n1, n2, n3 = 60, 140, 400
+    p = ops.make_params(90, n1, n2, n3, P=0.4, rhoE=0.18, seed=0xABCDEF0123)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    streams = np.array([0, 5, 2 ** 40 + 3], dtype=np.uint64)
+    G = np.stack([np.full(90, 0.16), 0.16 + 0.1 * aal90["map_ACh"] / aal90["map_ACh"].mean(), np.full(90, 0.3)])
+    sg = np.stack([np.full(90, 7.68), 7.68 - 0.1 * aal90["map_NA"] / aal90["map_NA"].mean(), np.full(90, 7.5)])
+    Y, fin = ops.wc_run(p, aal90["SC"], G, sg, B=3, streams=streams)
+    for b in range(3):
+        Yo = oracle_lib.wc_run(aal90["SC"], G[b], sg[b], n1, n2, n3, seed=0xABCDEF0123, stream=int(streams[b]), p=po)
+        assert np.max(np.abs(Y[b] - Yo) / np.abs(Yo)) < 1e-9
+        fo = oracle_lib.wc_run(aal90["SC"], G[b], sg[b], n1, n2, n3, seed=0xABCDEF0123, stream=int(streams[b]), p=po, want="final")
+        assert np.max(np.abs(fin[b] - fo) / np.abs(fo)) < 1e-9
+
+
+def test_wc_derivative_matches_oracle(aal90):
+    from nremmodfc_b200 import ops
+    from oracle import wc_oracle
+    rng = np.random.default_rng(3)
+    X = np.stack([rng.random(90) * 0.5, rng.random(90) * 0.5, 2 + rng.random(90)])
+    nz = rng.normal(0, 0.2, 90)
+    p = ops.make_params(90, 0, 0, 0, P=0.4, rhoE=0.18)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    d = ops.wc_derivative(p, aal90["SC"], X, 0.16, 7.68, noise=nz, tau_ip=2.0)
+    dE, dI, da = wc_oracle.derivative(X[0], X[1], X[2], aal90["SC"], 0.16, 7.68, nz, 2.0, po)
+    assert np.allclose(d, np.stack([dE, dI, da]), rtol=1e-12, atol=1e-13)
+
+
+def _synthetic_E(T, N, seed):
+    """E_t-like input: positive, band-limited fluctuations around 0.18 plus white noise."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(T)[:, None] * 0.002
+    slow = 0.03 * np.sin(2 * np.pi * (0.02 + 0.05 * rng.random(N))[None, :] * t * 20 + rng.random(N)[None, :] * 6)
+    walk = np.cumsum(rng.normal(0, 1, (T, N)), axis=0)
+    walk = 0.02 * (walk - walk.mean(0)) / (walk.std(0) + 1e-9)
+    return 0.18 + slow + walk + 0.05 * rng.random((T, N))
+
+
+@pytest.mark.parametrize("T,N,ds,Neq", [(300000, 90, 1000, 2000), (30011, 90, 10, 2000), (2100, 7, 3, 2000), (5000, 33, 97, 0)])
+def test_bold_filter_stage_matches_oracle(T, N, ds, Neq, oracle_lib):
+    """BOLDModel.Sim + cut/filtfilt/decimate at the reference's full size and at ragged sizes."""
+    from nremmodfc_b200 import ops
+    from nremmodfc_b200.sweep import bandpass_ba
+    from oracle import bold_oracle
+    E = _synthetic_E(T, N, seed=T)
+    bold = ops.bold_sim(E, 0.04)
+    bo = oracle_lib.bold_sim(E, 0.04)
+    assert np.max(np.abs(bold - bo)) < 1e-12 * max(1.0, np.max(np.abs(bo)))
+    b, a = bandpass_ba(0.04)
+    y = ops.filtfilt_decimate(bo, b, a, Neq=Neq, ds=ds)
+    yo = bold_oracle.filt_decimate(bo, ds, Neq, 0.04)
+    assert y.shape == yo.shape
+    assert np.max(np.abs(y - yo)) < 1e-6 * np.max(np.abs(yo))
+    if y.shape[0] > 8:
+        assert np.max(np.abs(ops.fc(y) - bold_oracle.fc(yo))) < 1e-6
+
+
+def test_filter_is_linear_and_batched():
+    """Size-independent property at the reference's full length: filt(a x + b y) = a filt(x) + b filt(y)."""
+    from nremmodfc_b200 import ops
+    from nremmodfc_b200.sweep import bandpass_ba
+    rng = np.random.default_rng(1)
+    x = np.cumsum(rng.normal(size=(2, 300000, 5)), axis=1) * 1e-3
+    b, a = bandpass_ba(0.04)
+    fx = ops.filtfilt_decimate(x, b, a)
+    fz = ops.filtfilt_decimate(2.0 * x[0] - 3.0 * x[1], b, a)
+    assert fx.shape == (2, 298, 5)
+    assert np.max(np.abs(fz - (2.0 * fx[0] - 3.0 * fx[1]))) < 1e-9 * np.max(np.abs(fz))
+
+
+def test_short_input_is_rejected():
+    from nremmodfc_b200 import ops
+    from nremmodfc_b200.sweep import bandpass_ba
+    b, a = bandpass_ba(0.04)
+    with pytest.raises(ValueError):
+        ops.filtfilt_decimate(np.zeros((2010, 3)), b, a)
+
+
+@pytest.mark.parametrize("N,J", [(90, 298), (90, 11), (17, 64), (128, 40)])
+def test_fc_matches_numpy(N, J):
+    from nremmodfc_b200 import ops
+    rng = np.random.default_rng(N + J)
+    x = rng.normal(size=(3, J, N)) @ (np.eye(N) + 0.3 * rng.normal(size=(N, N)))
+    fc = ops.fc(x)
+    for b in range(3):
+        assert np.max(np.abs(fc[b] - np.corrcoef(x[b].T))) < 1e-12
+    assert np.array_equal(fc, np.transpose(fc, (0, 2, 1)))
+
+
+@pytest.mark.parametrize("N", [90, 30, 7])
+def test_gof_matches_oracle(N, aal90):
+    from nremmodfc_b200 import ops
+    from oracle import bold_oracle
+    rng = np.random.default_rng(N)
+    if N == 90:
+        emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    else:
+        emp = np.stack([np.corrcoef(rng.normal(size=(N, 50)) + rng.normal(size=(1, 50))) for _ in range(2)])
+    sims = np.stack([np.corrcoef(rng.normal(size=(N, 40)) + 0.7 * rng.normal(size=(1, 40))) for _ in range(5)])
+    g, m = ops.gof(sims, emp)
+    for b in range(5):
+        assert abs(m[b] - sims[b].mean()) < 1e-13
+        for k in range(emp.shape[0]):
+            assert np.allclose(g[b, k], bold_oracle.get_all_metrics(sims[b], emp[k]), rtol=1e-10, atol=1e-12)
+    # identity: a matrix against itself
+    g2, _ = ops.gof(emp[0], emp[0])
+    assert np.allclose(g2[0, 0], [1.0, 0.0, 1.0, 0.0], atol=1e-12)
+
+
+@pytest.mark.parametrize("kernel", ["fma"])
+def test_integrator_f32_short_horizon_vs_oracle(kernel, aal90, oracle_lib):
+    """The float32 production integrator with in-kernel Philox against the float64 oracle on the SAME
+    counter-based stream: a few hundred steps, so float32 rounding (not chaos) bounds the error."""
+    from nremmodfc_b200 import ops
+    from oracle import wc_oracle
+    n1, n2, n3 = 50, 100, 200
+    seed = 77
+    p = ops.make_params(90, n1, n2, n3, P=0.4, rhoE=0.18, seed=seed)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    B = 131                                                    # ragged: 2 tiles, the second almost empty
+    rng = np.random.default_rng(0)
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    mG = np.stack([np.ones(90), aal90["map_ACh"] / aal90["map_ACh"].mean()])
+    mS = np.stack([np.ones(90), aal90["map_NA"] / aal90["map_NA"].mean()])
+    map_id = np.r_[np.zeros(128, np.int32), np.ones(3, np.int32)]
+    streams = rng.integers(0, 2 ** 62, B).astype(np.uint64)
+    E, fin = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, map_id, streams, kernel=kernel)
+    assert E.shape == (10, 90, B) and fin.shape == (3, 90, B)
+    for b in (0, 1, 31, 32, 77, 127, 128, 130):
+        m = map_id[b]
+        Yo, fo = wc_oracle.run(aal90["SC"], 0.16 + dG[b] * mG[m], 7.68 + ds[b] * mS[m], n1, n2, n3, seed=seed,
+                               streams=[int(streams[b])], p=po, return_final=True)
+        assert np.max(np.abs(E[:, :, b] - Yo[0, :, 0, :]) / np.abs(Yo[0, :, 0, :])) < 2e-4
+        assert np.max(np.abs(fin[:, :, b] - fo[0]) / np.abs(fo[0])) < 2e-4
+
+
+@pytest.mark.parametrize("kernel", ["fma"])
+def test_integrator_is_deterministic_and_layout_independent(kernel, aal90):
+    """Results depend on (seed, stream, parameters) only — not on the position inside the batch."""
+    from nremmodfc_b200 import ops
+    p = ops.make_params(90, 100, 200, 400, P=0.4, rhoE=0.18, seed=3)
+    B = 256
+    streams = np.arange(B, dtype=np.uint64)
+    dG = np.linspace(-0.1, 0.3, B)
+    E1, f1 = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=streams, kernel=kernel)
+    E2, f2 = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=streams, kernel=kernel)
+    assert np.array_equal(E1, E2) and np.array_equal(f1, f2)
+    perm = np.random.default_rng(0).permutation(B)[:100]
+    E3, f3 = ops.integrate_f32(p, aal90["SC"], np.full(100, 0.16), dG[perm], np.full(100, 7.68), np.zeros(100),
+                               streams=streams[perm], kernel=kernel)
+    assert np.array_equal(E3, E1[:, :, perm]) and np.array_equal(f3, f1[:, :, perm])
+
+
+@pytest.mark.parametrize("kernel,bold_f32", [("fma", False), ("fma", True)])
+def test_sweep_pipeline_vs_oracle(kernel, bold_f32, aal90, oracle_lib):
+    """Whole fused pipeline on a shortened run (1 s of recording) against the oracle pipeline."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle, wc_oracle
+    n1, n2, n3 = 200, 800, 10000
+    p = ops.make_params(90, n1, n2, n3, P=0.4, rhoE=0.18, seed=9)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    B = 140
+    dG, ds = np.linspace(-0.1, 0.3, B), np.linspace(0.2, -0.2, B)
+    streams = np.arange(B, dtype=np.uint64) * 7 + 1
+    out = sweep.sweep_gof(p, aal90["SC"], emp, np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams, want_fc=True,
+                          kernel=kernel, bold_f32=bold_f32, Neq=100, bold_downsamp=10, chunk_samples=37)
+    assert out["gof"].shape == (B, 4, 4) and out["fc"].shape == (B, 90, 90)
+    for k in (0, 63, 127, 128, 139):
+        E = oracle_lib.wc_run(aal90["SC"], 0.16 + dG[k], 7.68 + ds[k], n1, n2, n3, seed=9, stream=int(streams[k]), p=po, want="E")
+        FC = bold_oracle.fc(bold_oracle.filt_decimate(oracle_lib.bold_sim(E, 0.04), 10, 100, 0.04))
+        assert np.max(np.abs(FC - out["fc"][k])) < 5e-3
+        g = np.array([bold_oracle.get_all_metrics(out["fc"][k], emp[j]) for j in range(4)])
+        assert np.allclose(g, out["gof"][k], atol=1e-9)
+        assert abs(out["mean"][k] - out["fc"][k].mean()) < 1e-12

@@ -1,0 +1,165 @@
+"""CPU-only tests: the C-ABI library loads and exports what include/nremfc.h declares, host-side
+sweep logic, the drop-in module surface, and the 2-rank gloo gather.  No compute calls (no GPU)."""
+import itertools
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def built():
+    from nremmodfc_b200 import build
+    return build.build_library()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "nremfc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(nrem_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 16
+    from nremmodfc_b200 import _lib
+    assert declared == set(_lib.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.nrem_abi_version() == 1
+    nm = subprocess.run(["nm", "-D", "--defined-only", built], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", nm), f"{name} is not an exported text symbol"
+
+
+def test_library_is_built_for_sm100a(built):
+    out = subprocess.run(["cuobjdump", "-lelf", built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nremmodfc_b200 import _lib, ops
+    assert _lib.lib.nrem_device_count() == 0
+    with pytest.raises(_lib.NremError):
+        ops.fc(np.zeros((10, 4)))
+    import nremmodfc_b200.netwWilsonCowanPlastic as wc
+    with pytest.raises(_lib.NremError):
+        wc.run()
+
+
+def test_product_does_not_import_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "nremmodfc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                if re.search(r"^\s*(from|import)\s+oracle|oracle/", open(os.path.join(dirpath, f)).read(), flags=re.M):
+                    bad.append(f)
+    # comments may cite oracle/philox.py as the stream definition; imports / includes may not
+    for f in list(bad):
+        txt = open([os.path.join(d, f) for d, _, fs in os.walk(os.path.join(ROOT, "nremmodfc_b200")) if f in fs][0]).read()
+        if not re.search(r"^\s*(from|import)\s+oracle|#include.*oracle", txt, flags=re.M):
+            bad.remove(f)
+    assert not bad
+
+
+def test_module_surface_defaults(built):
+    """Same attribute names and defaults as netwWilsonCowanPlastic.py:23-68."""
+    import importlib
+    import nremmodfc_b200.netwWilsonCowanPlastic as wc
+    wc = importlib.reload(wc)
+    expect = dict(a_ee=3.5, a_ie_0=2.5, a_ei=3.75, a_ii=0, tauE=0.010, tauI=0.020, P=0.4, Q=0, rhoE=0.14, tau_ip=2,
+                  rE=0.5, rI=0.5, mu=1, sigmaE=4, sigmaI=4, tTrans1=600, tTrans2=600, tstop=600, dt=0.002,
+                  dtSim=0.0001, downsamp=20, D=0.002, sid=12, G=0.7, nnodes=90, N=90)
+    for k, v in expect.items():
+        assert getattr(wc, k) == v, k
+    assert abs(wc.sqdtD - 0.2) < 1e-15
+    assert wc.CM.shape == (90, 90)
+    assert len(wc.timeSim) == 6000000 and len(wc.time) == 300000
+    assert wc.run.recompile() is None and wc.wilsonCowan.recompile() is None
+    assert callable(wc.run) and callable(wc.simBOLD) and callable(wc.S)
+    assert abs(wc.S(1.0, 4.0, 1.0) - 0.5) < 1e-15
+
+
+def test_make_params_validation(built):
+    from nremmodfc_b200 import ops
+    p = ops.make_params(90, 1, 2, 3, P=0.4, rhoE=0.18, seed=2 ** 63 + 5)
+    assert (p.nnodes, p.n1, p.n2, p.n3, p.downsamp) == (90, 1, 2, 3, 20)
+    assert p.seed == 2 ** 63 + 5 and abs(p.sqdtD - 0.2) < 1e-15
+    with pytest.raises(ValueError):
+        ops.make_params(90, 1, 2, 3, nonsense=1)
+    with pytest.raises(ValueError):
+        ops.make_params(90, 1, 2, 3, tauE=np.ones(90))
+
+
+def test_product_grid_order(built):
+    from nremmodfc_b200 import sweep
+    seeds = np.arange(3)
+    dG = np.linspace(-0.1, 0.3, 4, endpoint=False)
+    dS = np.linspace(-0.2, 0.2, 5, endpoint=False)
+    s, g, sg = sweep.product_grid(seeds, dG, dS)
+    ref = list(itertools.product(seeds, dG, dS))                  # whole_sweep_both.py:61
+    assert len(s) == 60
+    for k, (a, b, c) in enumerate(ref):
+        assert (s[k], g[k], sg[k]) == (a, b, c)
+
+
+def test_shard_ids_match_reference_round_robin(built):
+    from nremmodfc_b200 import sweep
+    n, world = 1003, 8
+    seen = []
+    for r in range(world):
+        ids = sweep.shard_ids(n, r, world)
+        assert all(i % world == r for i in ids)                   # whole_sweep_both.py:64
+        seen.append(ids)
+    assert sorted(np.concatenate(seen)) == list(range(n))
+    cont = [sweep.shard_ids(n, r, world, contiguous=True) for r in range(world)]
+    assert np.array_equal(np.concatenate(cont), np.arange(n))
+
+
+def test_pad_by_map(built):
+    from nremmodfc_b200 import sweep
+    map_id = np.array([0] * 130 + [2] * 5 + [1] * 128)
+    src, valid = sweep.pad_by_map(map_id)
+    assert len(src) % 128 == 0 and len(src) == 256 + 128 + 128
+    tiles = map_id[src].reshape(-1, 128)
+    assert all(len(set(t)) == 1 for t in tiles)
+    assert sorted(src[valid]) == list(range(len(map_id)))
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from nremmodfc_b200 import sweep
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+n = 37
+ids = sweep.shard_ids(n, rank, world)
+rows = np.stack([ids * 10.0 + c for c in range(5)], axis=1)        # row content is a function of the global id
+table = sweep.gather_rows(ids, rows, n)
+expect = np.stack([np.arange(n) * 10.0 + c for c in range(5)], axis=1)
+assert np.array_equal(table, expect), table
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gather_gloo(built, tmp_path):
+    """World-size-2 run of the sharding + final gather (the only exchange on this path)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for r, pr in enumerate(procs):
+        out, _ = pr.communicate(timeout=180)
+        assert pr.returncode == 0, out
+        assert f"ok {r}" in out
