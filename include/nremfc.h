@@ -145,6 +145,12 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
                              const double* dsigma, const int32_t* h_map_id, const uint64_t* streams, int B,
                              int n_maps, int64_t nrec, float* E_samples, float* final_state, void* stream);
 
+/* Self-test of the tcgen05 contraction used by kernels 2/3: out[128,96] = E[128,96] x SCp[96,96]^T (float32,
+ * device pointers).  passes = 1 (TF32) or 3 (3xTF32).  The shared-memory descriptor fields (bytes) and the
+ * instruction descriptor can be overridden for diagnosis; 0 selects the library's own values.             */
+int nrem_selftest_tc_coupling(const float* E, const float* SCp, float* out, int passes, uint32_t lboA, uint32_t sboA,
+                              uint32_t lboB, uint32_t sboB, uint32_t idesc, void* stream);
+
 /* Kernel launches issued by this library on the calling thread since the last reset. */
 int64_t nrem_launch_count(int reset);
 

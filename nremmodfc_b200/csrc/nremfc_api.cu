@@ -487,4 +487,25 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     return NREM_OK;
 }
 
+int nrem_selftest_tc_coupling(const float* E, const float* SCp, float* out, int passes, uint32_t lboA, uint32_t sboA,
+                               uint32_t lboB, uint32_t sboB, uint32_t idesc, void* stream) {
+    NREM_REQUIRE(E && SCp && out, "null array");
+    NREM_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
+    if (!lboA) lboA = kLBO_A;
+    if (!sboA) sboA = kSBO;
+    if (!lboB) lboB = kLBO_B;
+    if (!sboB) sboB = kSBO;
+    if (!idesc) idesc = kIdescTf32;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (passes == 3) {
+        NREM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<3>()));
+        tc_selftest_kernel<3><<<1, kBatchThreads, tc_smem_bytes<3>(), st>>>(E, SCp, out, lboA, sboA, lboB, sboB, idesc);
+    } else {
+        NREM_CUDA(cudaFuncSetAttribute(tc_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
+        tc_selftest_kernel<1><<<1, kBatchThreads, tc_smem_bytes<1>(), st>>>(E, SCp, out, lboA, sboA, lboB, sboB, idesc);
+    }
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
 }  // extern "C"

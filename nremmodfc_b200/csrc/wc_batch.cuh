@@ -71,7 +71,7 @@ __device__ __forceinline__ void wc_node_update(const BatchConst& c, float& E, fl
 constexpr int kV0SmemBytes = kNPad * kNPad * 4 + 2 * (kNPad / 4) * kTile * 16 + 2 * kNPad * 4;
 
 __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_v0_kernel(const BatchArgs A) {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     float* SCs = reinterpret_cast<float*>(smraw);                               // [96][96]
     float4* Es = reinterpret_cast<float4*>(smraw + kNPad * kNPad * 4);          // [2][24][128]
     float* mG = reinterpret_cast<float*>(smraw + kNPad * kNPad * 4 + 2 * (kNPad / 4) * kTile * 16);

@@ -1,10 +1,328 @@
-// tcgen05 variant of the batched integrator (placeholder until the kernel lands).
+// tcgen05 variant of the batched integrator: the SC.E contraction of a 128-simulation tile is one
+// GEMM per Euler step,  D[128 sims, 96 nodes] = E[128, 96] x SC^T[96, 96],  issued by one thread as
+// tcgen05.mma (kind::tf32, M=128, N=96, K=8 per instruction) with both operands in shared memory
+// and the FP32 accumulator in tensor memory (TMEM).  TMEM lane = simulation, column = node, which
+// is exactly the lane=simulation register layout of wc_batch.cuh, so tcgen05.ld hands every
+// thread the coupling of its own (simulation, 24 nodes).
+//
+//   kernel 2 ("tc")  : operands rounded to TF32 (RN), 12 MMAs per step
+//   kernel 3 ("tc3") : 3xTF32 split  E = Eh + El, SC = Sh + Sl;  D = Eh.Sh + El.Sh + Eh.Sl
+//                      (36 MMAs per step, ~2^-21 relative error: FP32-grade coupling)
+//
+// Per step the MMA runs asynchronously while the threads draw the noise and advance I and a_ie
+// (none of which needs the coupling); only the E update waits for the accumulator.
+//
+// Shared-memory operand layout (no swizzle, K-major "interleaved" canonical form): 8x(16 B) core
+// matrices, address(m,k) = (m/8)*SBO + (m%8)*16 + (k/4)*LBO + (k%4)*4 with SBO = 128 B, i.e. the
+// tile is [k/4][row] float4 — threads of a warp (consecutive simulations) write consecutive
+// float4, conflict-free.
 #pragma once
 #include "wc_batch.cuh"
 
 namespace nrem {
-static int launch_wc_tc(int kernel, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
-    (void)kernel; (void)A; (void)tiles; (void)st;
-    return fail(NREM_ERR_UNSUPPORTED, "tcgen05 integrator not built%s%s");
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();      // a lost MMA completion must fail loudly, never hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 8 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+// wait for the loads; the registers are in/out operands so that no use can be hoisted above the wait
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :: "memory");
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell).  Offsets in bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+constexpr int kTcM = kTile;         // 128 simulations
+constexpr int kTcN = kNPad;         // 96 output nodes
+constexpr int kTcK = kNPad;         // 96 input nodes
+constexpr uint32_t kSBO = 128;                      // next 8-row group
+constexpr uint32_t kLBO_A = kTcM * 16;              // next 4-column group of A: 2048 B
+constexpr uint32_t kLBO_B = kTcN * 16;              // next 4-column group of B: 1536 B
+constexpr uint32_t kABytes = (kTcK / 4) * kLBO_A;   // 49152
+constexpr uint32_t kBBytes = (kTcK / 4) * kLBO_B;   // 36864
+constexpr uint32_t kTmemCols = 128;
+// instruction descriptor: D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9 / 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// Stage SC (padded [96][96] float32 in global) as the B operand(s).
+template <int NPASS>
+__device__ __forceinline__ void stage_b(const float* SCp, float* Bh, float* Bl, int tid, int nthreads) {
+    for (int idx = tid; idx < kTcN * kTcK; idx += nthreads) {
+        const int n = idx / kTcK, k = idx % kTcK;
+        const float v = SCp[idx];
+        const float h = tf32_rn(v);
+        const int o = (k >> 2) * (kLBO_B / 4) + n * 4 + (k & 3);
+        Bh[o] = h;
+        if (NPASS == 3) Bl[o] = v - h;
+    }
+}
+
+// One thread: issue the MMAs of one Euler step and commit them to `bar`.
+template <int NPASS>
+__device__ __forceinline__ void issue_coupling(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t tmem_d,
+                                               uint32_t lboA, uint32_t sboA, uint32_t lboB, uint32_t sboB, uint32_t idesc, uint64_t* bar) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+        const uint32_t a0 = (pass == 1) ? a_lo : a_hi;
+        const uint32_t b0 = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+        for (int kk = 0; kk < kTcK / 8; ++kk) {
+            const uint64_t ad = umma_desc(a0 + kk * 2 * kLBO_A, lboA, sboA);
+            const uint64_t bd = umma_desc(b0 + kk * 2 * kLBO_B, lboB, sboB);
+            umma_tf32(tmem_d, ad, bd, idesc, acc);
+            acc = 1;
+        }
+    }
+    umma_commit(bar);
+}
+
+template <int NPASS>
+constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kBBytes) + 2 * kNPad * 4 + 32; }
+
+template <int NPASS>
+__global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const BatchArgs A) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr bool SPLIT = NPASS == 3;
+    float* Ah = reinterpret_cast<float*>(smraw);
+    float* Al = reinterpret_cast<float*>(smraw + kABytes);
+    float* Bh = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes);
+    float* Bl = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes + kBBytes);
+    unsigned char* tail = smraw + (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+    float* mG = reinterpret_cast<float*>(tail);
+    float* mS = mG + kNPad;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tail + 2 * kNPad * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 2 * kNPad * 4 + 16);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = warp >> 2;
+    const int simt = ((warp & 3) << 5) | lane;
+    const int64_t sim = (int64_t)blockIdx.x * kTile + simt;
+    const BatchConst& c = A.c;
+    const int N = c.N;
+
+    stage_b<NPASS>(A.SCp, Bh, Bl, tid, kBatchThreads);
+    const int mid = A.tile_map[blockIdx.x];
+    if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
+    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    fence_proxy_async();                  // B tile (generic-proxy stores) -> visible to the tensor core's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * kChunk);
+
+    float E[kChunk], I[kChunk], a[kChunk];
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+        const int node = chunk * kChunk + k;
+        if (node < N) {
+            if (A.init) { E[k] = c.E0; I[k] = c.I0; a[k] = c.a0; }
+            else {
+                E[k] = A.state[(0 * (int64_t)N + node) * A.Bs + sim];
+                I[k] = A.state[(1 * (int64_t)N + node) * A.Bs + sim];
+                a[k] = A.state[(2 * (int64_t)N + node) * A.Bs + sim];
+            }
+        } else { E[k] = 0.f; I[k] = 0.f; a[k] = 0.f; }
+    }
+    const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
+    const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
+    const uint64_t strm = A.streams[sim];
+    const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
+    const uint32_t a_hi_u = smem_u32(Ah), a_lo_u = smem_u32(Al), b_hi_u = smem_u32(Bh), b_lo_u = smem_u32(Bl);
+    float4* Ah4 = reinterpret_cast<float4*>(Ah);
+    float4* Al4 = reinterpret_cast<float4*>(Al);
+    int rc = A.rec_phase;
+    int64_t row = A.row0;
+
+    for (int it = 0; it < A.nsteps; ++it) {
+        // 1. publish E(t) as the A operand
+#pragma unroll
+        for (int g = 0; g < kChunk / 4; ++g) {
+            const float4 v = make_float4(E[4 * g], E[4 * g + 1], E[4 * g + 2], E[4 * g + 3]);
+            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+            Ah4[(chunk * (kChunk / 4) + g) * kTile + simt] = h;
+            if (SPLIT) Al4[(chunk * (kChunk / 4) + g) * kTile + simt] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        fence_proxy_async();
+        tc_fence_before();                 // this thread's tcgen05.ld of the previous step precede the barrier
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_coupling<NPASS>(a_hi_u, a_lo_u, b_hi_u, b_lo_u, tmem_d, kLBO_A, kSBO, kLBO_B, kSBO, kIdescTf32, bar);
+        }
+        // 2. record E(t) (state BEFORE the update, netwWilsonCowanPlastic.py:129-130)
+        if (A.rec) {
+            if (rc == 0) {
+#pragma unroll
+                for (int k = 0; k < kChunk; ++k) {
+                    const int node = chunk * kChunk + k;
+                    if (node < N) A.Ebuf[(row * N + node) * A.Bs + sim] = E[k];
+                }
+                ++row;
+            }
+            if (++rc == A.downsamp) rc = 0;
+        }
+        // 3. everything that does not need the coupling, while the tensor core works
+        float xp[kChunk];
+        const uint32_t step = A.step0 + (uint32_t)it;
+#pragma unroll
+        for (int g = 0; g < kChunk / 4; ++g) {
+            float z[4];
+            normals4f(philox4x32_10(step, (uint32_t)(chunk * (kChunk / 4) + g), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * g + j;
+                float x = fmaf(c.a_ee, E[k], c.P);
+                x = fmaf(-a[k], I[k], x);
+                xp[k] = fmaf(c.sq, z[j], x);
+                const float y = fmaf(c.a_ei, E[k], -c.a_ii * I[k]);
+                const float SI = rcpf(1.0f + ex2f((y - c.mu) * c.sigI2));
+                a[k] = fmaf(A.kA, I[k] * (E[k] - c.rhoE), a[k]);
+                I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
+            }
+        }
+        // 4. coupling -> E(t+1)
+        mbar_wait(bar, (uint32_t)(it & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < kChunk / 8; ++h) {
+            uint32_t cr[8];
+            tmem_ld8(tmem_mine + 8 * h, cr);
+            tmem_ld_wait8(cr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * h + j;
+                const int node = chunk * kChunk + k;
+                const float Gi = fmaf(dG, mG[node], G0);
+                const float sg2 = fmaf(dsg, mS[node], sg0);
+                const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);
+                const float SE = rcpf(1.0f + ex2f((x - c.mu) * sg2));
+                E[k] = fmaf(c.kE, fmaf(fmaf(-c.rE, E[k], 1.0f), SE, -E[k]), E[k]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+        const int node = chunk * kChunk + k;
+        if (node < N) {
+            A.state[(0 * (int64_t)N + node) * A.Bs + sim] = E[k];
+            A.state[(1 * (int64_t)N + node) * A.Bs + sim] = I[k];
+            A.state[(2 * (int64_t)N + node) * A.Bs + sim] = a[k];
+        }
+    }
+}
+
+static int launch_wc_tc(int kernel, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
+    if (kernel == 3) {
+        NREM_CUDA(cudaFuncSetAttribute(wc_batch_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<3>()));
+        wc_batch_tc_kernel<3><<<(unsigned)tiles, kBatchThreads, tc_smem_bytes<3>(), st>>>(A);
+    } else {
+        NREM_CUDA(cudaFuncSetAttribute(wc_batch_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
+        wc_batch_tc_kernel<1><<<(unsigned)tiles, kBatchThreads, tc_smem_bytes<1>(), st>>>(A);
+    }
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
+// ---- self-test of the contraction alone --------------------------------------------------------
+// out[128][96] = E[128][96] x SC[96][96]^T through exactly the staging / descriptor / MMA / TMEM-load
+// code of the integrator.  The descriptor fields are arguments so that the encoding can be probed.
+template <int NPASS>
+__global__ void __launch_bounds__(kBatchThreads, 1) tc_selftest_kernel(const float* Ein, const float* SCp, float* out, uint32_t lboA,
+                                                                      uint32_t sboA, uint32_t lboB, uint32_t sboB, uint32_t idesc) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr bool SPLIT = NPASS == 3;
+    float* Ah = reinterpret_cast<float*>(smraw);
+    float* Al = reinterpret_cast<float*>(smraw + kABytes);
+    float* Bh = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes);
+    float* Bl = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes + kBBytes);
+    unsigned char* tail = smraw + (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tail + 2 * kNPad * 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 2 * kNPad * 4 + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = warp >> 2;
+    const int simt = ((warp & 3) << 5) | lane;
+    stage_b<NPASS>(SCp, Bh, Bl, tid, kBatchThreads);
+    for (int idx = tid; idx < kTcM * kTcK; idx += kBatchThreads) {
+        const int m = idx / kTcK, k = idx % kTcK;
+        const float v = Ein[idx], h = tf32_rn(v);
+        const int o = (k >> 2) * (kLBO_A / 4) + m * 4 + (k & 3);
+        Ah[o] = h;
+        if (SPLIT) Al[o] = v - h;
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    if (tid == 0) issue_coupling<NPASS>(smem_u32(Ah), smem_u32(Al), smem_u32(Bh), smem_u32(Bl), tmem_d, lboA, sboA, lboB, sboB, idesc, bar);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * kChunk);
+#pragma unroll
+    for (int h = 0; h < kChunk / 8; ++h) {
+        uint32_t cr[8];
+        tmem_ld8(tmem_mine + 8 * h, cr);
+        tmem_ld_wait8(cr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[simt * kTcN + chunk * kChunk + 8 * h + j] = __uint_as_float(cr[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
+}
+
 }  // namespace nrem

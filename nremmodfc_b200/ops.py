@@ -246,5 +246,20 @@ def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=No
         return E, d_fin[:, :, :B].cpu().numpy()
 
 
+def selftest_tc_coupling(E, SC, passes=1, lboA=0, sboA=0, lboB=0, sboB=0, idesc=0, device=None):
+    """out[128, 96] = E[128, 96] @ SC[96, 96].T through the tcgen05 path of the integrator (diagnostic)."""
+    dev = _device(device)
+    E = np.ascontiguousarray(E, dtype=np.float32)
+    SC = np.ascontiguousarray(SC, dtype=np.float32)
+    if E.shape != (128, 96) or SC.shape != (96, 96):
+        raise ValueError("E must be [128, 96] and SC [96, 96]")
+    with torch.cuda.device(dev):
+        d_E, d_S = to_device(E, torch.float32, dev), to_device(SC, torch.float32, dev)
+        d_o = torch.zeros((128, 96), dtype=torch.float32, device=dev)
+        check(lib.nrem_selftest_tc_coupling(_ptr(d_E), _ptr(d_S), _ptr(d_o), int(passes), lboA, sboA, lboB, sboB, idesc, _stream()))
+        torch.cuda.synchronize(dev)
+        return d_o.cpu().numpy()
+
+
 def launch_count(reset=False):
     return int(lib.nrem_launch_count(1 if reset else 0))
