@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: WC + BOLD + FC + GoF simulations per second on the reference's
+homogeneous G x sigma x 50-seed sweep (BASELINE.json configs[1]; whole_sweep_both.py grid).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the whole pipeline over the 20 000-simulation sweep (50 seeds x 20 dG x 20 dsigma,
+AAL90, full length 1 + 400 + 600 s = 10.01 M Euler steps each) through the public host API
+(`nremmodfc_b200.sweep.SweepPlan.run`: NumPy in, NumPy out).  Inside every timed step
+  * `e2e`   = wall clock of the API call (pinned H2D of SC/targets/parameters, D2H of the GoF table),
+  * `value` = the same pass timed on the device with CUDA events (inputs resident in HBM -> GoF in HBM).
+Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank runs its own 20 000-simulation sweep
+(seeds 50*rank ... 50*rank+49), no data-path collective, one final all-gather of the GoF table.
+`--impl reference` times the reference's CPU path (oracle port in C, one process per host core, the
+reference's own parallel model whole_sweep_both.py:23-24) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FULL = dict(n1=10_000, n2=4_000_000, n3=6_000_000)           # whole_sweep_both.py:43-50
+STEPS_PER_SIM = sum(FULL.values())
+FLOP_PER_STEP = 2 * 90 * 90 + 39 * 90                        # dense dgemv + elementwise
+NODE_SECONDS_PER_SIM = 1001 * 90
+METRIC = "WC+BOLD sims/sec (AAL90, 50-seed G x sigma sweep)"
+
+
+def load_inputs():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "aal90_inputs.npz"))
+    return d["SC"], np.stack([d[s] for s in ("W", "N1", "N2", "N3")])
+
+
+def sweep_grid(rank, n_sims):
+    """whole_sweep_both.py:57-61 with the committed table's grid (whole_sweep_both_maps.py:92-93)."""
+    from nremmodfc_b200 import sweep
+    seeds = np.arange(50) + 50 * rank
+    dG = np.linspace(-0.1, 0.3, 20, endpoint=False)
+    dS = np.linspace(-0.2, 0.2, 20, endpoint=False)
+    s, g, sg = sweep.product_grid(seeds, dG, dS)
+    return s[:n_sims], g[:n_sims], sg[:n_sims]
+
+
+# ---- CPU baseline (oracle port) ---------------------------------------------------------------
+def _cpu_worker(args):
+    seed, frac = args
+    from oracle import bold_oracle, cwrap, wc_oracle
+    SC, emp = load_inputs()
+    p = wc_oracle.params(P=0.4, rhoE=0.18)
+    n1, n2, n3 = int(FULL["n1"] * frac), int(FULL["n2"] * frac), int(FULL["n3"] * frac)
+    E = cwrap.wc_run(SC, 0.16, 7.68, n1, n2, n3, seed=1, stream=seed, p=p, want="E", fast_rng=True)
+    bold = cwrap.bold_sim(E, 0.04)
+    neq = min(2000, max(0, E.shape[0] - 1100))
+    y = bold_oracle.filt_decimate(bold, 1000 if E.shape[0] > 12000 else 100, neq, 0.04)
+    FC = bold_oracle.fc(y)
+    g = [bold_oracle.get_all_metrics(FC, emp[k]) for k in range(4)]
+    return float(g[0][0])
+
+
+def cpu_baseline(frac=0.05, reps=1):
+    """Times the oracle's C restatement of the reference pipeline on all host cores; returns sims/s of
+    FULL-length simulations (the cost is linear in the number of Euler steps)."""
+    import multiprocessing as mp
+    from oracle import cwrap
+    cwrap.build()
+    cores = os.cpu_count() or 1
+    tasks = [(i, frac) for i in range(cores * reps)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 0.0005)] * cores)          # warm: page in scipy, build tables
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, tasks, chunksize=1)
+        wall = time.perf_counter() - t0
+    sims_per_s = len(tasks) * frac / wall
+    return {"value": sims_per_s, "unit": "sims/s", "cores": cores, "kind": "port",
+            "sample": f"{len(tasks)} sims x {frac:g} of the 10.01M-step horizon (+BOLD/filter/FC/GoF), one process per core, "
+                      f"{wall:.1f} s wall; scaled linearly in steps",
+            "wall_s": wall}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(frac=args.cpu_frac)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    wall = float(np.mean([r["wall_s"] for r in vals]))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: homogeneous G x sigma sweep x 50 seeds (AAL90, 1+400+600 s)", "sample": vals[-1]["sample"]},
+            "cpu_baseline": {k: vals[-1][k] for k in ("unit", "cores", "kind", "sample")} | {"value": v},
+            "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "node_seconds_per_s": v * NODE_SECONDS_PER_SIM}
+    print(json.dumps(line))
+
+
+# ---- clocks ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median([float(r[0]) for r in rows])), "sm_max_mhz": float(rows[0][1]),
+                "power_w_median": float(np.median(pw)) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+# ---- our arm ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nremmodfc_b200 import ops, sweep
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    SC, emp = load_inputs()
+    B = args.sims
+    seeds, dG, dS = sweep_grid(rank, B)
+    # replicate id: unique per (seed, cell) over all ranks -> results do not depend on the sharding
+    streams = (seeds.astype(np.uint64) << np.uint64(32)) | np.arange(B, dtype=np.uint64) % np.uint64(400)
+    G0, s0 = np.full(B, 0.16), np.full(B, 7.68)                 # whole_sweep_both.py:30
+
+    scale = args.horizon_scale
+    pf = ops.make_params(90, int(FULL["n1"] * scale), int(FULL["n2"] * scale), int(FULL["n3"] * scale), P=0.4, rhoE=0.18, seed=2024)
+    pw = ops.make_params(90, 200, 40_000, 60_000, P=0.4, rhoE=0.18, seed=2024)     # warm-up pass: 1 % of the horizon
+    plan = sweep.SweepPlan(pf, B, kernel=args.kernel, bold_f32=not args.bold_f64, chunk_samples=args.chunk_samples)
+    warm = sweep.SweepPlan(pw, B, kernel=args.kernel, bold_f32=not args.bold_f64, chunk_samples=args.chunk_samples)
+    fma_peak, _ = ops.measure_fma_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        warm.run(SC, emp, G0, dG, s0, dS, streams)
+    warm.close()
+    barrier()
+    ops.launch_count(reset=True)
+    plan.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_ms, k1_ms, k1_launches, table = 0.0, 0.0, 0, None
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = plan.run(SC, emp, G0, dG, s0, dS, streams)
+        pr = plan.profile()
+        dev_ms += pr["total_ms"]
+        k1_ms += pr["integrator_ms"]
+        k1_launches += pr["integrator_launches"]
+        rows = np.concatenate([out["gof"].reshape(B, 16), out["mean"][:, None]], axis=1)
+        table = sweep.gather_rows(np.arange(B) + rank * B, rows, B * world) if world > 1 else rows
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    launches = ops.launch_count()
+    if world > 1:
+        t = torch.tensor([wall_ms, dev_ms, k1_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_ms, dev_ms, k1_ms = t.tolist()
+    total_sims = B * world * args.steps * scale
+    value = total_sims / (dev_ms * 1e-3)
+    e2e = total_sims / (wall_ms * 1e-3)
+    k1_flops = B * args.steps * scale * STEPS_PER_SIM * FLOP_PER_STEP          # algorithmic flop of one rank's launches
+    achieved = k1_flops / (k1_ms * 1e-3) / 1e12
+    if rank == 0:
+        ok = bool(np.isfinite(table).all())
+        line = {
+            "metric": METRIC, "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (integrator; coupling 3xTF32 on tcgen05) + f64 (filter/FC/GoF)" if args.kernel in ("auto", "tc3") else "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: homogeneous G x sigma sweep x 50 seeds = 20000 sims per GPU (AAL90 SC, "
+                                   "G0=0.16, sigma0=7.68, 1+400+600 s, GoF vs W/N1/N2/N3)",
+                       "sims_per_gpu": B, "euler_steps_per_sim": int(STEPS_PER_SIM * scale), "kernel": args.kernel,
+                       "bold_state": "f64" if args.bold_f64 else "f32", "horizon_scale": scale,
+                       "warmup_pass": "same batch, 1% of the horizon", "l2": "inputs are register/SMEM resident; each step streams "
+                       "its own E samples (> L2) through HBM", "results_finite": ok},
+            "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": plan.h2d_bytes, "d2h_bytes_per_step": plan.d2h_bytes},
+            "gpu_launches": int(launches),
+            "node_seconds_per_s": value * NODE_SECONDS_PER_SIM,
+            "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
+                         "traffic": None, "kernel": "wc_batch_tc_kernel" if args.kernel != "fma" else "wc_batch_v0_kernel",
+                         "algorithmic_flop_per_euler_step": FLOP_PER_STEP, "kernel_share_of_step": k1_ms / dev_ms,
+                         "launches": k1_launches, "avg_launch_ms": k1_ms / max(k1_launches, 1),
+                         "peak_source": "measured in this run: register-only FFMA chains on all SMs (nrem_measure_fma_peak)",
+                         "note": "the SC.E contraction runs on tcgen05 tensor cores, so the FP32-FMA roof can be exceeded"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cb = cpu_baseline(frac=args.cpu_frac)
+            cb.pop("wall_s", None)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sims", type=int, default=20000, help="simulations per GPU (default: the full 50 x 20 x 20 sweep)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fma", "tc", "tc3"])
+    ap.add_argument("--bold-f64", action="store_true")
+    ap.add_argument("--chunk-samples", type=int, default=0)
+    ap.add_argument("--horizon-scale", type=float, default=1.0, help="DEBUG ONLY: shorten every phase (numbers are then not bench values)")
+    ap.add_argument("--cpu-frac", type=float, default=0.05)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -137,6 +137,12 @@ int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, 
                    const int32_t* h_map_id, const uint64_t* streams, const double* emp,
                    double* gof, double* extra, double* fc, void* stream);
 
+/* Optional device-side timing of the next nrem_sweep_run calls (CUDA events on the caller's stream).
+ * nrem_sweep_get_profile blocks until the last run has finished and fills h_out[4] (host) with
+ * {whole pipeline ms, integrator kernels ms, integrator launches, reserved}.                      */
+int nrem_sweep_set_profiling(nrem_sweep_plan* plan, int on);
+int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out);
+
 /* Test hooks for the sweep's integrator: advance B simulations n1+n2+n3 steps with kernel
  * variant `kernel` and return the float32 E samples [nrec, N, Bpad] (Bpad = B rounded up to
  * NREM_TILE_SIMS, simulation fastest) and the final state [3, N, Bpad].                        */
@@ -150,6 +156,10 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
  * instruction descriptor can be overridden for diagnosis; 0 selects the library's own values.             */
 int nrem_selftest_tc_coupling(const float* E, const float* SCp, float* out, int passes, uint32_t lboA, uint32_t sboA,
                               uint32_t lboB, uint32_t sboB, uint32_t idesc, void* stream);
+
+/* Measures the FP32 FMA-pipe peak of the current device (register-only FMA chains on every SM, best of 3,
+ * ~20 ms each): the roofline denominator of the integrator.  Blocking.  h_tflops, h_ms: host.       */
+int nrem_measure_fma_peak(double* h_tflops, double* h_ms);
 
 /* Kernel launches issued by this library on the calling thread since the last reset. */
 int64_t nrem_launch_count(int reset);

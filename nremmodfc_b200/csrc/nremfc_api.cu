@@ -252,6 +252,10 @@ struct nrem_sweep_plan {
     uint64_t* streams;
     void* bw_state;
     double *bold_dec, *fc;
+    // optional timing of the integrator launches (CUDA events on the caller's stream)
+    bool prof_on;
+    std::vector<cudaEvent_t> ev;      // [0] pipeline start, [1] pipeline end, then (begin, end) per integrator launch
+    int ev_used;
 };
 
 static BatchConst make_const(const nrem_wc_params& p) {
@@ -267,7 +271,7 @@ static BatchConst make_const(const nrem_wc_params& p) {
 }
 
 static int resolve_kernel(int kernel) {
-    if (kernel == 0) return 1;
+    if (kernel == 0) return 3;      // auto = tcgen05 3xTF32
     return kernel;
 }
 
@@ -328,6 +332,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     nrem_sweep_plan* P = new (std::nothrow) nrem_sweep_plan();
     if (!P) return fail(NREM_ERR_ARG, "out of host memory%s%s");
     P->p = *p; P->o = *o; P->B = B; P->n_maps = n_maps; P->K = K; P->N = p->nnodes; P->dev = nullptr;
+    P->prof_on = false; P->ev_used = 0;
     P->Bs = round_up(B, kTile); P->tiles = P->Bs / kTile;
     P->T = (p->n3 + p->downsamp - 1) / p->downsamp;
     P->Tf = P->T - o->Neq;
@@ -372,6 +377,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
 int nrem_sweep_destroy(nrem_sweep_plan* plan) {
     if (!plan) return NREM_OK;
     if (plan->dev) cudaFree(plan->dev);
+    for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
     delete plan;
     return NREM_OK;
 }
@@ -401,7 +407,19 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
             const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
             if (Ebuf_all) { A.Ebuf = Ebuf_all; A.row0 = row_base; }
             else { A.Ebuf = d.Ebuf; A.row0 = 0; }
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (plan && plan->prof_on) {
+                while ((int)plan->ev.size() < plan->ev_used + 2) {
+                    cudaEvent_t e;
+                    NREM_CUDA(cudaEventCreate(&e));
+                    plan->ev.push_back(e);
+                }
+                e0 = plan->ev[plan->ev_used]; e1 = plan->ev[plan->ev_used + 1];
+                plan->ev_used += 2;
+                NREM_CUDA(cudaEventRecord(e0, st));
+            }
             if (int rc = launch_integrator(kernel, A, tiles, st)) return rc;
+            if (e1) NREM_CUDA(cudaEventRecord(e1, st));
             if (ph == 2 && plan) {
                 const int64_t nth = plan->nth;
                 const unsigned blocks = (unsigned)((nth + 127) / 128);
@@ -428,6 +446,11 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
     NREM_REQUIRE(CM && mapG && mapS && G0 && dG && sigma0 && dsigma && streams && emp && gof, "null array");
     cudaStream_t st = (cudaStream_t)stream;
     StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
+    if (P->prof_on) {
+        while (P->ev.size() < 2) { cudaEvent_t e; NREM_CUDA(cudaEventCreate(&e)); P->ev.push_back(e); }
+        P->ev_used = 2;
+        NREM_CUDA(cudaEventRecord(P->ev[0], st));
+    }
     if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st)) return rc;
     if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st)) return rc;
     const int N = P->N;
@@ -447,6 +470,32 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
         NREM_CUDA(cudaMemcpy2DAsync(extra, 4 * sizeof(double), meanfc, sizeof(double), sizeof(double), P->B,
                                     cudaMemcpyDeviceToDevice, st));
     }
+    if (P->prof_on) NREM_CUDA(cudaEventRecord(P->ev[1], st));
+    return NREM_OK;
+}
+
+int nrem_sweep_set_profiling(nrem_sweep_plan* plan, int on) {
+    NREM_REQUIRE(plan, "plan is null");
+    plan->prof_on = on != 0;
+    plan->ev_used = 0;
+    return NREM_OK;
+}
+
+int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out) {
+    NREM_REQUIRE(plan && h_out, "null argument");
+    NREM_REQUIRE(plan->prof_on && plan->ev_used >= 2, "profiling was not enabled for the last run");
+    NREM_CUDA(cudaEventSynchronize(plan->ev[1]));
+    float ms = 0.f;
+    NREM_CUDA(cudaEventElapsedTime(&ms, plan->ev[0], plan->ev[1]));
+    h_out[0] = ms;
+    double k1 = 0.0;
+    for (int i = 2; i + 1 < plan->ev_used; i += 2) {
+        NREM_CUDA(cudaEventElapsedTime(&ms, plan->ev[i], plan->ev[i + 1]));
+        k1 += ms;
+    }
+    h_out[1] = k1;
+    h_out[2] = (plan->ev_used - 2) / 2;
+    h_out[3] = 0.0;
     return NREM_OK;
 }
 
@@ -484,6 +533,51 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     cudaFree(dev);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(NREM_ERR_CUDA, "integrate: %s%s", cudaGetErrorString(e));
+    return NREM_OK;
+}
+
+// FP32 FMA-pipe peak: 8 independent dependent-chains per thread, register operands only.
+__global__ void __launch_bounds__(1024) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-6f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456f) out[0] = r;            // never true; keeps the chains alive
+}
+
+int nrem_measure_fma_peak(double* h_tflops, double* h_ms) {
+    NREM_REQUIRE(h_tflops && h_ms, "null argument");
+    int dev = 0, sms = 0;
+    NREM_CUDA(cudaGetDevice(&dev));
+    NREM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* d = nullptr;
+    NREM_CUDA(cudaMalloc(&d, 256));
+    cudaEvent_t e0, e1;
+    NREM_CUDA(cudaEventCreate(&e0));
+    NREM_CUDA(cudaEventCreate(&e1));
+    const int iters = 20000, blocks = sms * 2;
+    fma_peak_kernel<<<blocks, 1024>>>(d, 200, 0.999f, 0.001f);          // warm-up
+    NREM_LAUNCHED();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        NREM_CUDA(cudaEventRecord(e0));
+        fma_peak_kernel<<<blocks, 1024>>>(d, iters, 0.999f, 0.001f);
+        NREM_LAUNCHED();
+        NREM_CUDA(cudaEventRecord(e1));
+        NREM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        NREM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best;
+    }
+    const double flops = 2.0 * 128.0 * iters * (double)blocks * 1024.0;
+    *h_ms = best;
+    *h_tflops = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     return NREM_OK;
 }
 

@@ -261,5 +261,14 @@ def selftest_tc_coupling(E, SC, passes=1, lboA=0, sboA=0, lboB=0, sboB=0, idesc=
         return d_o.cpu().numpy()
 
 
+def measure_fma_peak(device=None):
+    """FP32 FMA peak of the device in TFLOP/s (register-only FMA chains; the integrator's roofline denominator)."""
+    dev = _device(device)
+    tf, ms = C.c_double(), C.c_double()
+    with torch.cuda.device(dev):
+        check(lib.nrem_measure_fma_peak(C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
 def launch_count(reset=False):
     return int(lib.nrem_launch_count(1 if reset else 0))

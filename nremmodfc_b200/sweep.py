@@ -112,6 +112,15 @@ class SweepPlan:
         T = (p.n3 + p.downsamp - 1) // p.downsamp
         self.J = (T - int(Neq) + int(bold_downsamp) - 1) // int(bold_downsamp)
 
+    def set_profiling(self, on=True):
+        check(lib.nrem_sweep_set_profiling(self._plan, 1 if on else 0))
+
+    def profile(self):
+        """Device times of the last run (blocks until it finished): dict(total_ms, integrator_ms, integrator_launches)."""
+        out = (C.c_double * 4)()
+        check(lib.nrem_sweep_get_profile(self._plan, out))
+        return {"total_ms": out[0], "integrator_ms": out[1], "integrator_launches": int(out[2])}
+
     def close(self):
         if self._plan:
             lib.nrem_sweep_destroy(self._plan)

@@ -31,7 +31,7 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.orc_wc_run.restype = C.c_int
         L.orc_wc_run.argtypes = [C.POINTER(WCParams), dp, C.c_int, dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int,
-                                 C.c_int64, dp, C.c_uint64, C.c_uint64, dp, dp, dp]
+                                 C.c_int64, dp, C.c_uint64, C.c_uint64, dp, dp, dp, C.c_int]
         L.orc_bold_sim.restype = C.c_int
         L.orc_bold_sim.argtypes = [dp, C.c_int64, C.c_int, C.c_double, dp]
         L.orc_philox_normals.restype = None
@@ -56,8 +56,9 @@ def c_params(p):
     return cp
 
 
-def wc_run(CM, G, sigmaE, n1, n2, n3, nrec=None, noise=None, seed=0, stream=0, p=None, want="Y"):
-    """One simulation.  want: "Y" -> [nrec,3,N], "E" -> [nrec,N], "final" -> [3,N]."""
+def wc_run(CM, G, sigmaE, n1, n2, n3, nrec=None, noise=None, seed=0, stream=0, p=None, want="Y", fast_rng=False):
+    """One simulation.  want: "Y" -> [nrec,3,N], "E" -> [nrec,N], "final" -> [3,N].
+    fast_rng=True (timed CPU baseline only) draws the noise with xoshiro + polar method instead of Philox."""
     p = wc_oracle.params() if p is None else p
     CM = np.ascontiguousarray(CM, dtype=np.float64)
     N = CM.shape[0]
@@ -74,7 +75,7 @@ def wc_run(CM, G, sigmaE, n1, n2, n3, nrec=None, noise=None, seed=0, stream=0, p
     fin = np.zeros((3, N))
     cp = c_params(p)
     rc = lib().orc_wc_run(C.byref(cp), _dp(CM), N, _dp(G), _dp(sg), n1, n2, n3, ds, nrec, _dp(noise),
-                          int(seed), int(stream), _dp(Y), _dp(Eo), _dp(fin))
+                          int(seed), int(stream), _dp(Y), _dp(Eo), _dp(fin), int(bool(fast_rng)))
     assert rc == 0
     return {"Y": Y, "E": Eo, "final": fin}[want]
 

@@ -69,13 +69,36 @@ void orc_philox_normals(uint64_t seed, uint64_t stream, uint32_t step, int N, do
     }
 }
 
+/* Fast CPU noise for the timed baseline only (bench.py): xoshiro256** + Marsaglia polar method, the same
+ * algorithm class as the reference's generator (numba: MT19937 + polar Gaussian).  Never used for parity. */
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline uint64_t xo_next(uint64_t s[4]) {
+    const uint64_t r = rotl64(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+    return r;
+}
+static inline void polar_normals(uint64_t st[4], int N, double scale, double* z) {
+    int i = 0;
+    while (i < N) {
+        double u, v, r2;
+        do {
+            u = 2.0 * ((double)(xo_next(st) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+            v = 2.0 * ((double)(xo_next(st) >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+            r2 = u * u + v * v;
+        } while (r2 >= 1.0 || r2 == 0.0);
+        const double f = scale * sqrt(-2.0 * log(r2) / r2);
+        z[i++] = u * f;
+        if (i < N) z[i++] = v * f;
+    }
+}
+
 static inline double Sg(double x, double sigma, double mu) { return 1.0 / (1.0 + exp(-(x - mu) * sigma)); }
 
 /* CM [N,N] row-major; G, sigmaE [N]; noise NULL (philox) or [n1+n2+n3, N] already scaled by sqdtD.
  * Y   NULL or [nrec, 3, N]; Eonly NULL or [nrec, N] (E rows only); final NULL or [3, N]. */
 int orc_wc_run(const orc_wc_params* p, const double* CM, int N, const double* G, const double* sigmaE,
                int64_t n1, int64_t n2, int64_t n3, int downsamp, int64_t nrec, const double* noise,
-               uint64_t seed, uint64_t stream, double* Y, double* Eonly, double* final) {
+               uint64_t seed, uint64_t stream, double* Y, double* Eonly, double* final, int fast_rng) {
     double* buf = (double*)malloc(sizeof(double) * (size_t)N * 8);
     if (!buf) return -1;
     double *E = buf, *I = buf + N, *a = buf + 2 * N, *c = buf + 3 * N, *nz = buf + 4 * N;
@@ -83,6 +106,8 @@ int orc_wc_run(const orc_wc_params* p, const double* CM, int N, const double* G,
     for (int i = 0; i < N; ++i) { E[i] = p->E0; I[i] = p->I0; a[i] = p->a_ie_0; }
     const int64_t ns[3] = {n1, n2, n3};
     int64_t step = 0;
+    uint64_t xst[4] = {seed ^ 0x9E3779B97F4A7C15ull, stream + 0xBF58476D1CE4E5B9ull, 0x94D049BB133111EBull, 0x2545F4914F6CDD1Dull};
+    for (int i = 0; i < 16; ++i) xo_next(xst);
     for (int ph = 0; ph < 3; ++ph) {
         const double tau_ip = p->tau_ip[ph];
         for (int64_t it = 0; it < ns[ph]; ++it, ++step) {
@@ -99,15 +124,22 @@ int orc_wc_run(const orc_wc_params* p, const double* CM, int N, const double* G,
             }
             if (noise) {
                 memcpy(nz, noise + step * N, sizeof(double) * N);
+            } else if (fast_rng) {
+                polar_normals(xst, N, p->sqdtD, nz);
             } else {
                 orc_philox_normals(seed, stream, (uint32_t)step, N, nz);
                 for (int i = 0; i < N; ++i) nz[i] *= p->sqdtD;
             }
             for (int i = 0; i < N; ++i) {
                 const double* row = CM + (size_t)i * N;
-                double acc = 0.0;
-                for (int j = 0; j < N; ++j) acc += row[j] * E[j];
-                c[i] = acc;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;     /* 4 partial sums: lets the compiler vectorise */
+                int j = 0;
+                for (; j + 3 < N; j += 4) {
+                    a0 += row[j] * E[j]; a1 += row[j + 1] * E[j + 1];
+                    a2 += row[j + 2] * E[j + 2]; a3 += row[j + 3] * E[j + 3];
+                }
+                for (; j < N; ++j) a0 += row[j] * E[j];
+                c[i] = (a0 + a1) + (a2 + a3);
             }
             for (int i = 0; i < N; ++i) {
                 dE[i] = (-E[i] + (1 - p->rE * E[i]) * Sg(p->a_ee * E[i] - a[i] * I[i] + G[i] * c[i] + p->P + nz[i], sigmaE[i], p->mu)) / p->tauE;
