@@ -139,7 +139,7 @@ int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, 
 
 /* Optional device-side timing of the next nrem_sweep_run calls (CUDA events on the caller's stream).
  * nrem_sweep_get_profile blocks until the last run has finished and fills h_out[4] (host) with
- * {whole pipeline ms, integrator kernels ms, integrator launches, reserved}.                      */
+ * {whole pipeline ms, integrator ms of tile group 0, its launches, number of tile groups}.                      */
 int nrem_sweep_set_profiling(nrem_sweep_plan* plan, int on);
 int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out);
 

@@ -7,4 +7,10 @@ Layout
   netwWilsonCowanPlastic.py   drop-in for the reference module of the same name
   BOLDModel.py, utils.py      drop-ins for the reference's BOLDModel.Sim and utils.get_all_metrics
 """
+import os as _os
+
+# sweeps with more tiles than SMs run one stream per tile group (csrc/nremfc_api.cu:integrate); give every
+# stream its own hardware queue.  Only effective if set before the CUDA context exists.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 __all__ = ["ops", "sweep", "netwWilsonCowanPlastic", "BOLDModel", "utils"]

@@ -223,13 +223,14 @@ __global__ void filt_backward_kernel(FiltCoef f, FiltScratch S, int64_t nslots, 
     }
 }
 
-// Sweep path: consume `rows` float32 E samples [rows][N][Bs] (simulation fastest), advance the
-// Balloon-Windkessel state and the forward filter.  slot = node*Bs + sim.
+// Sweep path: consume `rows` float32 E samples [rows][N][Bs] (simulation fastest) of the simulations
+// [sim0, sim0 + nsim), advance the Balloon-Windkessel state and the forward filter.  slot = node*Bs + sim.
 template <typename BT>
-__global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t row_base, int N, int64_t Bs, int64_t Neq,
-                                         BT dt, BT* bw_state /*[4][nth]*/, FiltCoef f, FiltScratch S) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= (int64_t)N * Bs) return;
+__global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t row_base, int N, int64_t Bs, int64_t sim0, int64_t nsim,
+                                         int64_t Neq, BT dt, BT* bw_state /*[4][nth]*/, FiltCoef f, FiltScratch S) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)N * nsim) return;
+    const int64_t slot = (t / nsim) * Bs + sim0 + (t % nsim);
     BW<BT> bw;
     if (row_base == 0) {
         bw.init();

@@ -253,6 +253,12 @@ struct nrem_sweep_plan {
     void* bw_state;
     double *bold_dec, *fc;
     // optional timing of the integrator launches (CUDA events on the caller's stream)
+    // tile groups: more tiles than SMs are run as independent streams so that the hardware block
+    // scheduler keeps every SM busy across chunk boundaries (see integrate())
+    int last_groups;
+    std::vector<cudaStream_t> gstreams;
+    std::vector<cudaEvent_t> gjoin;
+    cudaEvent_t gfork;
     bool prof_on;
     std::vector<cudaEvent_t> ev;      // [0] pipeline start, [1] pipeline end, then (begin, end) per integrator launch
     int ev_used;
@@ -332,7 +338,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     nrem_sweep_plan* P = new (std::nothrow) nrem_sweep_plan();
     if (!P) return fail(NREM_ERR_ARG, "out of host memory%s%s");
     P->p = *p; P->o = *o; P->B = B; P->n_maps = n_maps; P->K = K; P->N = p->nnodes; P->dev = nullptr;
-    P->prof_on = false; P->ev_used = 0;
+    P->prof_on = false; P->ev_used = 0; P->gfork = nullptr; P->last_groups = 1;
     P->Bs = round_up(B, kTile); P->tiles = P->Bs / kTile;
     P->T = (p->n3 + p->downsamp - 1) / p->downsamp;
     P->Tf = P->T - o->Neq;
@@ -378,6 +384,9 @@ int nrem_sweep_destroy(nrem_sweep_plan* plan) {
     if (!plan) return NREM_OK;
     if (plan->dev) cudaFree(plan->dev);
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->gjoin) cudaEventDestroy(e);
+    for (cudaStream_t g : plan->gstreams) cudaStreamDestroy(g);
+    if (plan->gfork) cudaEventDestroy(plan->gfork);
     delete plan;
     return NREM_OK;
 }
@@ -386,6 +395,12 @@ int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan) { return plan ? pla
 
 // Runs phases 1-3; when Ebuf_all != NULL every sample goes to it (test hook), otherwise the
 // samples of each chunk are consumed by the BOLD/filter kernel of the plan.
+//
+// Scheduling: a tile (128 simulations) occupies one SM for a whole launch.  With more tiles than SMs a
+// single grid would need two waves per launch, the second almost empty; instead the tiles are split into
+// groups of <= 8, each with its own stream and its own chain  K1(chunk 0) -> K2(chunk 0) -> K1(chunk 1) ...
+// Chains are independent, so whenever one group's CTAs retire, waiting CTAs of any other group take the
+// SMs: the sweep costs tiles/SMs "rounds" instead of ceil(tiles/SMs).
 static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, int64_t Bs, int chunk_samples,
                      float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st) {
     BatchArgs A;
@@ -393,6 +408,25 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
     A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
     A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp;
     const int64_t tiles = Bs / kTile;
+    int dev = 0, sms = 148;
+    NREM_CUDA(cudaGetDevice(&dev));
+    NREM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int ngroups = 1;
+    if (plan && tiles > sms) ngroups = (int)std::min<int64_t>((tiles + 7) / 8, 30);
+    if (plan) plan->last_groups = ngroups;
+    std::vector<cudaStream_t> gs(1, st);
+    if (ngroups > 1) {
+        while ((int)plan->gstreams.size() < ngroups) {
+            cudaStream_t g; cudaEvent_t e;
+            NREM_CUDA(cudaStreamCreateWithFlags(&g, cudaStreamNonBlocking));
+            NREM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            plan->gstreams.push_back(g); plan->gjoin.push_back(e);
+        }
+        if (!plan->gfork) NREM_CUDA(cudaEventCreateWithFlags(&plan->gfork, cudaEventDisableTiming));
+        NREM_CUDA(cudaEventRecord(plan->gfork, st));
+        gs.assign(plan->gstreams.begin(), plan->gstreams.begin() + ngroups);
+        for (cudaStream_t g : gs) NREM_CUDA(cudaStreamWaitEvent(g, plan->gfork, 0));
+    }
     const int64_t ns[3] = {p.n1, p.n2, p.n3};
     const int64_t chunk_steps = (int64_t)chunk_samples * p.downsamp;
     int64_t step = 0;
@@ -407,32 +441,42 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
             const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
             if (Ebuf_all) { A.Ebuf = Ebuf_all; A.row0 = row_base; }
             else { A.Ebuf = d.Ebuf; A.row0 = 0; }
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (plan && plan->prof_on) {
-                while ((int)plan->ev.size() < plan->ev_used + 2) {
-                    cudaEvent_t e;
-                    NREM_CUDA(cudaEventCreate(&e));
-                    plan->ev.push_back(e);
+            for (int g = 0; g < ngroups; ++g) {
+                const int64_t t0 = tiles * g / ngroups, t1 = tiles * (g + 1) / ngroups;
+                A.tile0 = (int)t0;
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (plan && plan->prof_on && g == 0) {
+                    while ((int)plan->ev.size() < plan->ev_used + 2) {
+                        cudaEvent_t e;
+                        NREM_CUDA(cudaEventCreate(&e));
+                        plan->ev.push_back(e);
+                    }
+                    e0 = plan->ev[plan->ev_used]; e1 = plan->ev[plan->ev_used + 1];
+                    plan->ev_used += 2;
+                    NREM_CUDA(cudaEventRecord(e0, gs[g]));
                 }
-                e0 = plan->ev[plan->ev_used]; e1 = plan->ev[plan->ev_used + 1];
-                plan->ev_used += 2;
-                NREM_CUDA(cudaEventRecord(e0, st));
-            }
-            if (int rc = launch_integrator(kernel, A, tiles, st)) return rc;
-            if (e1) NREM_CUDA(cudaEventRecord(e1, st));
-            if (ph == 2 && plan) {
-                const int64_t nth = plan->nth;
-                const unsigned blocks = (unsigned)((nth + 127) / 128);
-                if (plan->o.bold_f32)
-                    bold_filter_chunk_kernel<float><<<blocks, 128, 0, st>>>(d.Ebuf, rows, row_base, plan->N, Bs, plan->o.Neq,
-                                                                         (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S);
-                else
-                    bold_filter_chunk_kernel<double><<<blocks, 128, 0, st>>>(d.Ebuf, rows, row_base, plan->N, Bs, plan->o.Neq,
-                                                                          plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S);
-                NREM_LAUNCHED();
+                if (int rc = launch_integrator(kernel, A, t1 - t0, gs[g])) return rc;
+                if (e1) NREM_CUDA(cudaEventRecord(e1, gs[g]));
+                if (ph == 2 && plan) {
+                    const int64_t sim0 = t0 * kTile, nsim = (t1 - t0) * kTile;
+                    const unsigned blocks = (unsigned)((plan->N * nsim + 127) / 128);
+                    if (plan->o.bold_f32)
+                        bold_filter_chunk_kernel<float><<<blocks, 128, 0, gs[g]>>>(d.Ebuf, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
+                                                                                (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S);
+                    else
+                        bold_filter_chunk_kernel<double><<<blocks, 128, 0, gs[g]>>>(d.Ebuf, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
+                                                                                 plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S);
+                    NREM_LAUNCHED();
+                }
             }
             step += n;
             first = false;
+        }
+    }
+    if (ngroups > 1) {
+        for (int g = 0; g < ngroups; ++g) {
+            NREM_CUDA(cudaEventRecord(plan->gjoin[g], gs[g]));
+            NREM_CUDA(cudaStreamWaitEvent(st, plan->gjoin[g], 0));
         }
     }
     return NREM_OK;
@@ -495,7 +539,7 @@ int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out) {
     }
     h_out[1] = k1;
     h_out[2] = (plan->ev_used - 2) / 2;
-    h_out[3] = 0.0;
+    h_out[3] = (double)plan->last_groups;
     return NREM_OK;
 }
 

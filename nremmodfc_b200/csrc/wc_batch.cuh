@@ -38,6 +38,7 @@ struct BatchArgs {
     const int32_t* tile_map;   // [Bs/128]
     const uint64_t* streams;   // [Bs]
     int64_t Bs;
+    int tile0;                 // first tile of this launch (tile = tile0 + blockIdx.x)
     uint32_t step0;            // global Euler step index of the first step of this launch
     int nsteps;
     int init;                  // 1: start from (E0, I0, a_ie_0) instead of loading state
@@ -79,12 +80,13 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_v0_kernel(const Bat
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = warp >> 2;
     const int simt = ((warp & 3) << 5) | lane;
-    const int64_t sim = (int64_t)blockIdx.x * kTile + simt;
+    const int tile = A.tile0 + (int)blockIdx.x;
+    const int64_t sim = (int64_t)tile * kTile + simt;
     const BatchConst& c = A.c;
     const int N = c.N;
 
     for (int k = tid; k < kNPad * kNPad; k += kBatchThreads) SCs[k] = A.SCp[k];
-    const int mid = A.tile_map[blockIdx.x];
+    const int mid = A.tile_map[tile];
     if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
 
     float E[kChunk], I[kChunk], a[kChunk];

@@ -143,12 +143,13 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = warp >> 2;
     const int simt = ((warp & 3) << 5) | lane;
-    const int64_t sim = (int64_t)blockIdx.x * kTile + simt;
+    const int tile = A.tile0 + (int)blockIdx.x;
+    const int64_t sim = (int64_t)tile * kTile + simt;
     const BatchConst& c = A.c;
     const int N = c.N;
 
     stage_b<NPASS>(A.SCp, Bh, Bl, tid, kBatchThreads);
-    const int mid = A.tile_map[blockIdx.x];
+    const int mid = A.tile_map[tile];
     if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
     if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
     if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }

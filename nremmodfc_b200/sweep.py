@@ -119,7 +119,7 @@ class SweepPlan:
         """Device times of the last run (blocks until it finished): dict(total_ms, integrator_ms, integrator_launches)."""
         out = (C.c_double * 4)()
         check(lib.nrem_sweep_get_profile(self._plan, out))
-        return {"total_ms": out[0], "integrator_ms": out[1], "integrator_launches": int(out[2])}
+        return {"total_ms": out[0], "integrator_ms": out[1], "integrator_launches": int(out[2]), "tile_groups": int(out[3])}
 
     def close(self):
         if self._plan:

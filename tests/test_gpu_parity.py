@@ -261,11 +261,11 @@ def test_sweep_pipeline_vs_oracle(kernel, bold_f32, aal90, oracle_lib):
     for k in (0, 63, 127, 128, 139):
         Eo = oracle_lib.wc_run(aal90["SC"], 0.16 + dG[k], 7.68 + ds[k], n1, n2, n3, seed=9, stream=int(streams[k]), p=po, want="E")
         # (a) float32 vs float64 on the same stream.  A float32 numpy emulation of the reference loop already
-        # differs from float64 by 2e-5 after 0.1 s and 3e-3 after 1.1 s (chaotic transient; measured on the GPU:
-        # 5.5e-5 and 1.2e-2 for "fma" and "tc3" alike), so: tight at the first recorded row, loose at the end.
+        # differs from float64 by 2e-5 after 0.1 s and 3e-3 after 1.1 s at G = 0.16 (chaotic transient; on the GPU
+        # 5.5e-5 / 1.2e-2 for "fma" and "tc3" alike) and reaches O(1) at the strongly coupled end of the grid, so
+        # only the first recorded row (0.1 s) is a meaningful trajectory check here.
         rel = np.abs(Eg[:, :, k] - Eo) / np.maximum(np.abs(Eo), 0.05)
         assert rel[0].max() < (5e-3 if kernel == "tc" else 5e-4)
-        assert rel.max() < 0.1
         E = Eg[:, :, k].astype(np.float64)
         FC = bold_oracle.fc(bold_oracle.filt_decimate(oracle_lib.bold_sim(E, 0.04), 10, 100, 0.04))
         assert np.max(np.abs(FC - out["fc"][k])) < (2e-2 if bold_f32 else 1e-6)        # (b)
@@ -286,3 +286,27 @@ def test_tcgen05_contraction(passes, tol, aal90):
     out = ops.selftest_tc_coupling(E, SC, passes=passes)
     exact = E.astype(np.float64) @ SC.astype(np.float64).T
     assert np.max(np.abs(out - exact)) < tol * np.max(np.abs(exact))
+
+
+def test_sweep_with_more_tiles_than_sms(aal90):
+    """More 128-tiles than SMs switches the host scheduler to independent tile-group streams; the results must
+    not depend on it (same simulations in a small single-stream batch give identical numbers)."""
+    import torch
+    from nremmodfc_b200 import ops, sweep
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = (sms + 3) * 128 - 5
+    p = ops.make_params(90, 100, 300, 2400, P=0.4, rhoE=0.18, seed=11)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    rng = np.random.default_rng(5)
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    streams = rng.integers(0, 2 ** 60, B).astype(np.uint64)
+    kw = dict(Neq=40, bold_downsamp=5, chunk_samples=50, bold_f32=True)
+    plan = sweep.SweepPlan(p, B, **kw)
+    plan.set_profiling(True)
+    big = plan.run(aal90["SC"], emp, np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams)
+    assert plan.profile()["tile_groups"] > 1
+    plan.close()
+    pick = np.r_[0:40, B - 300:B]
+    small = sweep.sweep_gof(p, aal90["SC"], emp, np.full(len(pick), 0.16), dG[pick], np.full(len(pick), 7.68), ds[pick], streams[pick], **kw)
+    assert np.isfinite(big["gof"]).all()
+    assert np.array_equal(big["gof"][pick], small["gof"]) and np.array_equal(big["mean"][pick], small["mean"])
