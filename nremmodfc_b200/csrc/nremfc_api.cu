@@ -1,6 +1,7 @@
 // C ABI of libnremfc (see include/nremfc.h).  Host-side orchestration only: argument checks,
 // filter-coefficient preparation, scratch carving and kernel launches.  No CPU compute fallback.
 #include <algorithm>
+#include <cstdlib>
 #include <complex>
 #include <new>
 #include <vector>
@@ -276,6 +277,13 @@ static BatchConst make_const(const nrem_wc_params& p) {
     return c;
 }
 
+// nodes per thread of the tcgen05 integrator (24/16/12); NREM_TC_NODES_PER_THREAD overrides for experiments
+static int g_nodes_per_thread = []() {
+    const char* e = getenv("NREM_TC_NODES_PER_THREAD");
+    const int v = e ? atoi(e) : 24;
+    return (v == 12 || v == 16) ? v : 24;
+}();
+
 static int resolve_kernel(int kernel) {
     if (kernel == 0) return 3;      // auto = tcgen05 3xTF32
     return kernel;
@@ -290,7 +298,7 @@ static int launch_integrator(int kernel, const BatchArgs& A, int64_t tiles, cuda
             break;
         case 2:
         case 3:
-            return launch_wc_tc(resolve_kernel(kernel), A, tiles, st);
+            return launch_wc_tc(resolve_kernel(kernel), g_nodes_per_thread, A, tiles, st);
         default:
             return fail(NREM_ERR_ARG, "unknown integrator kernel%s%s");
     }

@@ -103,33 +103,48 @@ __device__ __forceinline__ void stage_b(const float* SCp, float* Bh, float* Bl, 
     }
 }
 
-// One thread: issue the MMAs of one Euler step and commit them to `bar`.
+// One elected thread: issue the MMAs of one Euler step and commit them to `bar`.  adesc/bdesc are the
+// descriptors of the first K-slice; the next slice is 2 four-column groups further (start-address field += bytes/16).
 template <int NPASS>
-__device__ __forceinline__ void issue_coupling(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t tmem_d,
-                                               uint32_t lboA, uint32_t sboA, uint32_t lboB, uint32_t sboB, uint32_t idesc, uint64_t* bar) {
+__device__ __forceinline__ void issue_coupling(uint64_t ad_hi, uint64_t ad_lo, uint64_t bd_hi, uint64_t bd_lo, uint32_t tmem_d,
+                                               uint32_t idesc, uint64_t* bar) {
     uint32_t acc = 0;
 #pragma unroll
     for (int pass = 0; pass < NPASS; ++pass) {
-        const uint32_t a0 = (pass == 1) ? a_lo : a_hi;
-        const uint32_t b0 = (pass == 2) ? b_lo : b_hi;
+        const uint64_t a0 = (pass == 1) ? ad_lo : ad_hi;
+        const uint64_t b0 = (pass == 2) ? bd_lo : bd_hi;
 #pragma unroll
         for (int kk = 0; kk < kTcK / 8; ++kk) {
-            const uint64_t ad = umma_desc(a0 + kk * 2 * kLBO_A, lboA, sboA);
-            const uint64_t bd = umma_desc(b0 + kk * 2 * kLBO_B, lboB, sboB);
-            umma_tf32(tmem_d, ad, bd, idesc, acc);
+            umma_tf32(tmem_d, a0 + (uint64_t)(kk * ((2 * kLBO_A) >> 4)), b0 + (uint64_t)(kk * ((2 * kLBO_B) >> 4)), idesc, acc);
             acc = 1;
         }
     }
     umma_commit(bar);
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void named_bar_arrive(int nthreads) { asm volatile("bar.arrive 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+
 template <int NPASS>
 constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kBBytes) + 2 * kNPad * 4 + 32; }
 
-template <int NPASS>
-__global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const BatchArgs A) {
+// CH = nodes per thread (24, 16 or 12): the CTA has (96/CH) * 4 warps.
+template <int NPASS, int CH>
+__global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(const BatchArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr bool SPLIT = NPASS == 3;
+    constexpr int NT = (kNPad / CH) * kTile;
+    constexpr int NCHUNK = kNPad / CH;
     float* Ah = reinterpret_cast<float*>(smraw);
     float* Al = reinterpret_cast<float*>(smraw + kABytes);
     float* Bh = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes);
@@ -147,8 +162,11 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
     const int64_t sim = (int64_t)tile * kTile + simt;
     const BatchConst& c = A.c;
     const int N = c.N;
+    // The MMA issuer is a warp of the LAST chunk: that chunk holds the padding nodes (96 - N), whose work is
+    // skipped, so the issue slot costs no wall time.  Everybody else only *arrives* at the "A tile ready" barrier.
+    const bool issuer_warp = warp == 4 * (NCHUNK - 1);
 
-    stage_b<NPASS>(A.SCp, Bh, Bl, tid, kBatchThreads);
+    stage_b<NPASS>(A.SCp, Bh, Bl, tid, NT);
     const int mid = A.tile_map[tile];
     if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
     if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
@@ -158,12 +176,12 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
-    const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * kChunk);
+    const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * CH);
 
-    float E[kChunk], I[kChunk], a[kChunk];
+    float E[CH], I[CH], a[CH];
 #pragma unroll
-    for (int k = 0; k < kChunk; ++k) {
-        const int node = chunk * kChunk + k;
+    for (int k = 0; k < CH; ++k) {
+        const int node = chunk * CH + k;
         if (node < N) {
             if (A.init) { E[k] = c.E0; I[k] = c.I0; a[k] = c.a0; }
             else {
@@ -177,34 +195,39 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
     const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
     const uint64_t strm = A.streams[sim];
     const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
-    const uint32_t a_hi_u = smem_u32(Ah), a_lo_u = smem_u32(Al), b_hi_u = smem_u32(Bh), b_lo_u = smem_u32(Bl);
+    const uint64_t ad_hi = umma_desc(smem_u32(Ah), kLBO_A, kSBO), ad_lo = umma_desc(smem_u32(Al), kLBO_A, kSBO);
+    const uint64_t bd_hi = umma_desc(smem_u32(Bh), kLBO_B, kSBO), bd_lo = umma_desc(smem_u32(Bl), kLBO_B, kSBO);
     float4* Ah4 = reinterpret_cast<float4*>(Ah);
     float4* Al4 = reinterpret_cast<float4*>(Al);
+    const int nquads = (N + 3) >> 2;      // quads at or beyond this hold only padding nodes
     int rc = A.rec_phase;
     int64_t row = A.row0;
 
     for (int it = 0; it < A.nsteps; ++it) {
         // 1. publish E(t) as the A operand
 #pragma unroll
-        for (int g = 0; g < kChunk / 4; ++g) {
+        for (int g = 0; g < CH / 4; ++g) {
             const float4 v = make_float4(E[4 * g], E[4 * g + 1], E[4 * g + 2], E[4 * g + 3]);
             const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            Ah4[(chunk * (kChunk / 4) + g) * kTile + simt] = h;
-            if (SPLIT) Al4[(chunk * (kChunk / 4) + g) * kTile + simt] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            Ah4[(chunk * (CH / 4) + g) * kTile + simt] = h;
+            if (SPLIT) Al4[(chunk * (CH / 4) + g) * kTile + simt] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         }
         fence_proxy_async();
         tc_fence_before();                 // this thread's tcgen05.ld of the previous step precede the barrier
-        __syncthreads();
-        if (tid == 0) {
+        if (issuer_warp) {
+            named_bar_sync(NT);            // every warp has published its slice and drained its TMEM loads
             tc_fence_after();
-            issue_coupling<NPASS>(a_hi_u, a_lo_u, b_hi_u, b_lo_u, tmem_d, kLBO_A, kSBO, kLBO_B, kSBO, kIdescTf32, bar);
+            if (elect_one()) issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
+            __syncwarp();
+        } else {
+            named_bar_arrive(NT);
         }
         // 2. record E(t) (state BEFORE the update, netwWilsonCowanPlastic.py:129-130)
         if (A.rec) {
             if (rc == 0) {
 #pragma unroll
-                for (int k = 0; k < kChunk; ++k) {
-                    const int node = chunk * kChunk + k;
+                for (int k = 0; k < CH; ++k) {
+                    const int node = chunk * CH + k;
                     if (node < N) A.Ebuf[(row * N + node) * A.Bs + sim] = E[k];
                 }
                 ++row;
@@ -212,41 +235,51 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
             if (++rc == A.downsamp) rc = 0;
         }
         // 3. everything that does not need the coupling, while the tensor core works
-        float xp[kChunk];
+        float xp[CH];
         const uint32_t step = A.step0 + (uint32_t)it;
 #pragma unroll
-        for (int g = 0; g < kChunk / 4; ++g) {
-            float z[4];
-            normals4f(philox4x32_10(step, (uint32_t)(chunk * (kChunk / 4) + g), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+        for (int g = 0; g < CH / 4; ++g) {
+            const int q = chunk * (CH / 4) + g;
+            if (q < nquads) {              // warp-uniform: skips the padding quads of the last chunk
+                float z[4];
+                normals4f(philox4x32_10(step, (uint32_t)q, s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 4 * g + j;
-                float x = fmaf(c.a_ee, E[k], c.P);
-                x = fmaf(-a[k], I[k], x);
-                xp[k] = fmaf(c.sq, z[j], x);
-                const float y = fmaf(c.a_ei, E[k], -c.a_ii * I[k]);
-                const float SI = rcpf(1.0f + ex2f((y - c.mu) * c.sigI2));
-                a[k] = fmaf(A.kA, I[k] * (E[k] - c.rhoE), a[k]);
-                I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * g + j;
+                    float x = fmaf(c.a_ee, E[k], c.P);
+                    x = fmaf(-a[k], I[k], x);
+                    xp[k] = fmaf(c.sq, z[j], x);
+                    const float y = fmaf(c.a_ei, E[k], -c.a_ii * I[k]);
+                    const float SI = rcpf(1.0f + ex2f((y - c.mu) * c.sigI2));
+                    a[k] = fmaf(A.kA, I[k] * (E[k] - c.rhoE), a[k]);
+                    I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xp[4 * g + j] = 0.f;
             }
         }
         // 4. coupling -> E(t+1)
         mbar_wait(bar, (uint32_t)(it & 1));
         tc_fence_after();
 #pragma unroll
-        for (int h = 0; h < kChunk / 8; ++h) {
+        for (int h = 0; h < (CH + 7) / 8; ++h) {
             uint32_t cr[8];
-            tmem_ld8(tmem_mine + 8 * h, cr);
+            if (8 * h + 8 <= CH) tmem_ld8(tmem_mine + 8 * h, cr); else tmem_ld4(tmem_mine + 8 * h, cr);
             tmem_ld_wait8(cr);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = 8 * h + j;
-                const int node = chunk * kChunk + k;
-                const float Gi = fmaf(dG, mG[node], G0);
-                const float sg2 = fmaf(dsg, mS[node], sg0);
-                const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);
-                const float SE = rcpf(1.0f + ex2f((x - c.mu) * sg2));
-                E[k] = fmaf(c.kE, fmaf(fmaf(-c.rE, E[k], 1.0f), SE, -E[k]), E[k]);
+                if (k < CH) {
+                    const int node = chunk * CH + k;
+                    if ((node >> 2) < nquads) {
+                        const float Gi = fmaf(dG, mG[node], G0);
+                        const float sg2 = fmaf(dsg, mS[node], sg0);
+                        const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);
+                        const float SE = rcpf(1.0f + ex2f((x - c.mu) * sg2));
+                        E[k] = fmaf(c.kE, fmaf(fmaf(-c.rE, E[k], 1.0f), SE, -E[k]), E[k]);
+                    }
+                }
             }
         }
     }
@@ -254,8 +287,8 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
 #pragma unroll
-    for (int k = 0; k < kChunk; ++k) {
-        const int node = chunk * kChunk + k;
+    for (int k = 0; k < CH; ++k) {
+        const int node = chunk * CH + k;
         if (node < N) {
             A.state[(0 * (int64_t)N + node) * A.Bs + sim] = E[k];
             A.state[(1 * (int64_t)N + node) * A.Bs + sim] = I[k];
@@ -264,16 +297,24 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_tc_kernel(const Bat
     }
 }
 
-static int launch_wc_tc(int kernel, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
-    if (kernel == 3) {
-        NREM_CUDA(cudaFuncSetAttribute(wc_batch_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<3>()));
-        wc_batch_tc_kernel<3><<<(unsigned)tiles, kBatchThreads, tc_smem_bytes<3>(), st>>>(A);
-    } else {
-        NREM_CUDA(cudaFuncSetAttribute(wc_batch_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
-        wc_batch_tc_kernel<1><<<(unsigned)tiles, kBatchThreads, tc_smem_bytes<1>(), st>>>(A);
-    }
+template <int NPASS, int CH>
+static int launch_wc_tc_t(const BatchArgs& A, int64_t tiles, cudaStream_t st) {
+    NREM_CUDA(cudaFuncSetAttribute(wc_batch_tc_kernel<NPASS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<NPASS>()));
+    wc_batch_tc_kernel<NPASS, CH><<<(unsigned)tiles, (kNPad / CH) * kTile, tc_smem_bytes<NPASS>(), st>>>(A);
     NREM_LAUNCHED();
     return NREM_OK;
+}
+
+// kernel: 2 = TF32, 3 = 3xTF32; nodes_per_thread: 24 (16 warps), 16 (24 warps) or 12 (32 warps)
+static int launch_wc_tc(int kernel, int nodes_per_thread, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
+    if (kernel == 3) {
+        if (nodes_per_thread == 12) return launch_wc_tc_t<3, 12>(A, tiles, st);
+        if (nodes_per_thread == 16) return launch_wc_tc_t<3, 16>(A, tiles, st);
+        return launch_wc_tc_t<3, 24>(A, tiles, st);
+    }
+    if (nodes_per_thread == 12) return launch_wc_tc_t<1, 12>(A, tiles, st);
+    if (nodes_per_thread == 16) return launch_wc_tc_t<1, 16>(A, tiles, st);
+    return launch_wc_tc_t<1, 24>(A, tiles, st);
 }
 
 // ---- self-test of the contraction alone --------------------------------------------------------
@@ -309,7 +350,10 @@ __global__ void __launch_bounds__(kBatchThreads, 1) tc_selftest_kernel(const flo
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
-    if (tid == 0) issue_coupling<NPASS>(smem_u32(Ah), smem_u32(Al), smem_u32(Bh), smem_u32(Bl), tmem_d, lboA, sboA, lboB, sboB, idesc, bar);
+    if (warp == 0 && elect_one())
+        issue_coupling<NPASS>(umma_desc(smem_u32(Ah), lboA, sboA), umma_desc(smem_u32(Al), lboA, sboA), umma_desc(smem_u32(Bh), lboB, sboB),
+                              umma_desc(smem_u32(Bl), lboB, sboB), tmem_d, idesc, bar);
+    __syncwarp();
     mbar_wait(bar, 0);
     tc_fence_after();
     const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * kChunk);
