@@ -161,6 +161,9 @@ int nrem_selftest_tc_coupling(const float* E, const float* SCp, float* out, int 
  * ~20 ms each): the roofline denominator of the integrator.  Blocking.  h_tflops, h_ms: host.       */
 int nrem_measure_fma_peak(double* h_tflops, double* h_ms);
 
+/* Device time (CUDA events) of the integrator launches of the last nrem_sweep_integrate_f32 call on this thread. */
+double nrem_last_integrate_ms(void);
+
 /* Kernel launches issued by this library on the calling thread since the last reset. */
 int64_t nrem_launch_count(int reset);
 

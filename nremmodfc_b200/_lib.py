@@ -14,7 +14,7 @@ ABI_SYMBOLS = [
     "nrem_abi_version", "nrem_last_error", "nrem_device_count", "nrem_wc_run_f64", "nrem_wc_derivative_f64",
     "nrem_bold_sim_f64", "nrem_filt_scratch_bytes", "nrem_filtfilt_decimate_f64", "nrem_fc_f64", "nrem_gof_f64",
     "nrem_sweep_create", "nrem_sweep_destroy", "nrem_sweep_device_bytes", "nrem_sweep_run",
-    "nrem_sweep_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
+    "nrem_sweep_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
 ]
 
 
@@ -46,6 +46,7 @@ lib.nrem_abi_version.restype = _i
 lib.nrem_last_error.restype = C.c_char_p
 lib.nrem_device_count.restype = _i
 lib.nrem_launch_count.restype = _i64
+lib.nrem_last_integrate_ms.restype = _d
 lib.nrem_launch_count.argtypes = [_i]
 lib.nrem_wc_run_f64.argtypes = [C.POINTER(WCParams), _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]
 lib.nrem_wc_derivative_f64.argtypes = [C.POINTER(WCParams), _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp]
@@ -67,7 +68,7 @@ lib.nrem_sweep_get_profile.argtypes = [_vp, C.POINTER(_d)]
 lib.nrem_selftest_tc_coupling.argtypes = [_vp, _vp, _vp, _i] + [C.c_uint32] * 5 + [_vp]
 for _n in ABI_SYMBOLS:
     getattr(lib, _n)          # AttributeError here = the library does not export what include/nremfc.h declares
-    if _n not in ("nrem_last_error", "nrem_launch_count", "nrem_filt_scratch_bytes", "nrem_sweep_device_bytes"):
+    if _n not in ("nrem_last_integrate_ms", "nrem_last_error", "nrem_launch_count", "nrem_filt_scratch_bytes", "nrem_sweep_device_bytes"):
         getattr(lib, _n).restype = _i
 
 if lib.nrem_abi_version() != 1:

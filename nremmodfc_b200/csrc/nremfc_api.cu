@@ -16,6 +16,7 @@
 namespace nrem {
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+static thread_local double g_last_integrate_ms = 0.0;
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
@@ -123,6 +124,8 @@ int nrem_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+double nrem_last_integrate_ms(void) { return g_last_integrate_ms; }
+
 int64_t nrem_launch_count(int reset) {
     const int64_t v = g_launches;
     if (reset) g_launches = 0;
@@ -577,11 +580,17 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     StagePtrs d{final_state, (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
                 (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
     int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
     if (rc == NREM_OK) {
+        cudaEventRecord(t0, st);
         if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st);
         else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st);   // samples go to a scratch ring
+        cudaEventRecord(t1, st);
     }
     cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == NREM_OK && e == cudaSuccess) { float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1); g_last_integrate_ms = ms; }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
     cudaFree(dev);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(NREM_ERR_CUDA, "integrate: %s%s", cudaGetErrorString(e));

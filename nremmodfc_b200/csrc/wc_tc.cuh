@@ -127,8 +127,6 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
     return p != 0;
 }
-__device__ __forceinline__ void named_bar_arrive(int nthreads) { asm volatile("bar.arrive 1, %0;" ::"r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -139,12 +137,14 @@ template <int NPASS>
 constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kBBytes) + 2 * kNPad * 4 + 32; }
 
 // CH = nodes per thread (24, 16 or 12): the CTA has (96/CH) * 4 warps.
+// Measured alternatives that LOST on B200 (profiles/r01_kernel_variants.md): an elected issuer warp with a
+// bar.arrive/bar.sync split (+6 %), skipping the padding quads with warp-uniform branches (+37 %: the branches
+// stop the compiler from interleaving quads), 16 or 12 nodes per thread (+2 %).
 template <int NPASS, int CH>
 __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(const BatchArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr bool SPLIT = NPASS == 3;
     constexpr int NT = (kNPad / CH) * kTile;
-    constexpr int NCHUNK = kNPad / CH;
     float* Ah = reinterpret_cast<float*>(smraw);
     float* Al = reinterpret_cast<float*>(smraw + kABytes);
     float* Bh = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes);
@@ -162,9 +162,6 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const int64_t sim = (int64_t)tile * kTile + simt;
     const BatchConst& c = A.c;
     const int N = c.N;
-    // The MMA issuer is a warp of the LAST chunk: that chunk holds the padding nodes (96 - N), whose work is
-    // skipped, so the issue slot costs no wall time.  Everybody else only *arrives* at the "A tile ready" barrier.
-    const bool issuer_warp = warp == 4 * (NCHUNK - 1);
 
     stage_b<NPASS>(A.SCp, Bh, Bl, tid, NT);
     const int mid = A.tile_map[tile];
@@ -199,7 +196,6 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const uint64_t bd_hi = umma_desc(smem_u32(Bh), kLBO_B, kSBO), bd_lo = umma_desc(smem_u32(Bl), kLBO_B, kSBO);
     float4* Ah4 = reinterpret_cast<float4*>(Ah);
     float4* Al4 = reinterpret_cast<float4*>(Al);
-    const int nquads = (N + 3) >> 2;      // quads at or beyond this hold only padding nodes
     int rc = A.rec_phase;
     int64_t row = A.row0;
 
@@ -214,13 +210,10 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
         }
         fence_proxy_async();
         tc_fence_before();                 // this thread's tcgen05.ld of the previous step precede the barrier
-        if (issuer_warp) {
-            named_bar_sync(NT);            // every warp has published its slice and drained its TMEM loads
+        __syncthreads();                   // every warp has published its slice and drained its TMEM loads
+        if (tid == 0) {
             tc_fence_after();
-            if (elect_one()) issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
-            __syncwarp();
-        } else {
-            named_bar_arrive(NT);
+            issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
         }
         // 2. record E(t) (state BEFORE the update, netwWilsonCowanPlastic.py:129-130)
         if (A.rec) {
@@ -240,7 +233,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
 #pragma unroll
         for (int g = 0; g < CH / 4; ++g) {
             const int q = chunk * (CH / 4) + g;
-            if (q < nquads) {              // warp-uniform: skips the padding quads of the last chunk
+            {
                 float z[4];
                 normals4f(philox4x32_10(step, (uint32_t)q, s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
 #pragma unroll
@@ -254,9 +247,6 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
                     a[k] = fmaf(A.kA, I[k] * (E[k] - c.rhoE), a[k]);
                     I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xp[4 * g + j] = 0.f;
             }
         }
         // 4. coupling -> E(t+1)
@@ -272,7 +262,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
                 const int k = 8 * h + j;
                 if (k < CH) {
                     const int node = chunk * CH + k;
-                    if ((node >> 2) < nquads) {
+                    {
                         const float Gi = fmaf(dG, mG[node], G0);
                         const float sg2 = fmaf(dsg, mS[node], sg0);
                         const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);

@@ -270,5 +270,9 @@ def measure_fma_peak(device=None):
     return tf.value, ms.value
 
 
+def last_integrate_ms():
+    return float(lib.nrem_last_integrate_ms())
+
+
 def launch_count(reset=False):
     return int(lib.nrem_launch_count(1 if reset else 0))

@@ -1,5 +1,6 @@
 """Drop-in for the GoF part of the reference's utils.py (lines 18-50)."""
 import numpy as np
+from scipy import signal
 
 from . import ops
 
@@ -27,3 +28,19 @@ def new_metric(flat1, flat2):
     """utils.py:28-31."""
     flat1, flat2 = np.asarray(flat1, dtype=np.float64), np.asarray(flat2, dtype=np.float64)
     return float(1 - np.corrcoef(flat1, flat2)[0, 1] + (flat1.mean() - flat2.mean()) ** 2)
+
+
+def kuramoto(sign):
+    """utils.py:34-40 — Kuramoto order parameter of the Hilbert phases: (mean, std) over time.
+
+    298 x 90 samples per simulation: host-side for now."""
+    analytic = signal.hilbert(np.asarray(sign, dtype=np.float64), axis=0)
+    k = np.abs(np.mean(np.exp(1j * np.angle(analytic)), axis=1))
+    return float(k.mean()), float(k.std())
+
+
+# node groups of the reference (utils.py:52-57)
+thal = [38, 51]
+subL, subR = [35, 36, 37, 38], [51, 52, 53, 54]
+sub = subL + subR
+cortex = [i for i in range(90) if i not in sub]

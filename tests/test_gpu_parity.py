@@ -310,3 +310,58 @@ def test_sweep_with_more_tiles_than_sms(aal90):
     small = sweep.sweep_gof(p, aal90["SC"], emp, np.full(len(pick), 0.16), dG[pick], np.full(len(pick), 7.68), ds[pick], streams[pick], **kw)
     assert np.isfinite(big["gof"]).all()
     assert np.array_equal(big["gof"][pick], small["gof"]) and np.array_equal(big["mean"][pick], small["mean"])
+
+
+def test_driver_loop_through_compat_modules(aal90, tmp_path):
+    """The call sequence of whole_sweep_both.py:39-116 (set attributes, recompile, run, simBOLD, corrcoef,
+    get_all_metrics, kuramoto, one TSV row) through the compat/ module names, on a shortened horizon."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    np.savetxt(tmp_path / "SC_opti_25julio.txt", aal90["SC"])
+    os.makedirs(tmp_path / "empirical", exist_ok=True)
+    for s in ("W", "N1", "N2", "N3"):
+        np.savetxt(tmp_path / "empirical" / f"mean_mat_{s}_8dic24.txt", aal90[s])
+    script = r'''
+import numpy as np, os, itertools
+import netwWilsonCowanPlastic as wc
+import BOLDModel as BD
+from scipy import signal
+from skimage.metrics import structural_similarity as ssim
+import utils
+rank=int(os.environ['SLURM_ARRAY_TASK_ID']); threads=int(os.environ['SLURM_ARRAY_TASK_MAX'])+1
+struct = np.loadtxt("SC_opti_25julio.txt")
+states = ("W","N1","N2","N3")
+empFCW,empFCN1,empFCN2,empFCN3 = [np.loadtxt(f"empirical/mean_mat_{s}_8dic24.txt") for s in states]
+wc.P = 0.4; wc.rhoE = 0.18; wc.CM = struct
+wc.tTrans1=0.05; wc.tTrans2=0.5
+wc.timeTrans1=np.arange(0,wc.tTrans1,wc.dtSim); wc.timeTrans2=np.arange(0,wc.tTrans2,wc.dtSim)
+tstop = 9; wc.tstop = tstop
+wc.timeSim=np.arange(0,tstop,wc.dtSim); wc.time=np.arange(0,tstop,wc.dt)
+rows = []
+for sim,(seed,dG,dS) in enumerate(itertools.product([0,1],[0.0],[0.0, 0.02])):
+    if sim%threads == rank:
+        wc.sid = seed
+        wc.G = 0.16 + dG; wc.sigmaE = 7.68 + dS; wc.nnodes = 90
+        wc.run.recompile()
+        tray = wc.run()
+        E_t = tray[:,0,:]
+        BOLD = wc.simBOLD(E_t,nnodes=90,BOLD_downsamp=100)
+        sFC = np.corrcoef(BOLD.T)
+        m = [utils.get_all_metrics(sFC,e,data_range=1) for e in (empFCW,empFCN1,empFCN2,empFCN3)]
+        sync,meta = utils.kuramoto(BOLD)
+        rows.append((seed, dS, m[0][0], m[0][1], ssim(sFC, empFCW, data_range=1), m[0][2], sync, meta, float(np.mean(sFC)), tray.shape, BOLD.shape))
+for r in rows: print(repr(r))
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "compat"), root]), SLURM_ARRAY_TASK_ID="0", SLURM_ARRAY_TASK_MAX="0")
+    r = subprocess.run([sys.executable, "-c", script], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = [eval(l) for l in r.stdout.strip().splitlines()]
+    assert len(rows) == 4
+    for row in rows:
+        assert row[-2] == (4500, 3, 90) and row[-1] == (25, 90)
+        assert abs(row[4] - row[5]) < 1e-12                     # skimage shim == gof kernel's ssim
+        assert all(np.isfinite(row[2:9]))
+    # sid is a real seed here: same (seed, cell) would reproduce; different seeds differ
+    assert rows[0][2] != rows[2][2]
