@@ -280,13 +280,6 @@ static BatchConst make_const(const nrem_wc_params& p) {
     return c;
 }
 
-// nodes per thread of the tcgen05 integrator (24/16/12); NREM_TC_NODES_PER_THREAD overrides for experiments
-static int g_nodes_per_thread = []() {
-    const char* e = getenv("NREM_TC_NODES_PER_THREAD");
-    const int v = e ? atoi(e) : 24;
-    return (v == 12 || v == 16) ? v : 24;
-}();
-
 static int resolve_kernel(int kernel) {
     if (kernel == 0) return 3;      // auto = tcgen05 3xTF32
     return kernel;
@@ -301,7 +294,7 @@ static int launch_integrator(int kernel, const BatchArgs& A, int64_t tiles, cuda
             break;
         case 2:
         case 3:
-            return launch_wc_tc(resolve_kernel(kernel), g_nodes_per_thread, A, tiles, st);
+            return launch_wc_tc(resolve_kernel(kernel), A.homo != 0, A, tiles, st);
         default:
             return fail(NREM_ERR_ARG, "unknown integrator kernel%s%s");
     }
@@ -318,7 +311,7 @@ struct StagePtrs {
 // Copies/convert the float64 API arrays into the padded float32 device layout.
 static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, const double* CM, const double* mapG,
                         const double* mapS, const double* G0, const double* dG, const double* s0, const double* ds,
-                        const int32_t* h_map_id, const uint64_t* streams, const StagePtrs& d, cudaStream_t st) {
+                        const int32_t* h_map_id, const uint64_t* streams, const StagePtrs& d, cudaStream_t st, int* homo) {
     const int N = p.nnodes;
     std::vector<int32_t> tm((size_t)(Bs / kTile));
     for (int64_t t = 0; t < Bs / kTile; ++t) {
@@ -335,6 +328,17 @@ static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, 
     NREM_LAUNCHED();
     stage_maps_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(mapG, mapS, n_maps, N, d.mapG, d.mapS);
     NREM_LAUNCHED();
+    {   // homogeneous sweep (every map entry exactly 1)?  Decided once per sweep on the staged float32 maps.
+        int* dflag = nullptr;
+        int one = 1;
+        NREM_CUDA(cudaMalloc(&dflag, sizeof(int)));
+        NREM_CUDA(cudaMemcpyAsync(dflag, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        maps_all_ones_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(d.mapG, d.mapS, n_maps, N, dflag);
+        NREM_LAUNCHED();
+        NREM_CUDA(cudaMemcpyAsync(homo, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        NREM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(dflag);
+    }
     stage_par_kernel<<<(unsigned)((Bs + 255) / 256), 256, 0, st>>>(G0, dG, s0, ds, streams, B, Bs, d.par, d.streams);
     NREM_LAUNCHED();
     return NREM_OK;
@@ -413,11 +417,11 @@ int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan) { return plan ? pla
 // Chains are independent, so whenever one group's CTAs retire, waiting CTAs of any other group take the
 // SMs: the sweep costs tiles/SMs "rounds" instead of ceil(tiles/SMs).
 static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, int64_t Bs, int chunk_samples,
-                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st) {
+                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st, int homo) {
     BatchArgs A;
     A.c = make_const(p);
     A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
-    A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp;
+    A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp; A.homo = homo;
     const int64_t tiles = Bs / kTile;
     int dev = 0, sms = 148;
     NREM_CUDA(cudaGetDevice(&dev));
@@ -506,8 +510,9 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
         P->ev_used = 2;
         NREM_CUDA(cudaEventRecord(P->ev[0], st));
     }
-    if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st)) return rc;
-    if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st)) return rc;
+    int homo = 0;
+    if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, &homo)) return rc;
+    if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st, homo)) return rc;
     const int N = P->N;
     filt_backward_kernel<<<(unsigned)((P->nth + 127) / 128), 128, 0, st>>>(P->fh.f, P->S, P->nth, N, P->Bs, 1, P->bold_dec,
                                                                          P->J * N, N, 1, P->B);
@@ -579,13 +584,14 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     char* base = (char*)dev;
     StagePtrs d{final_state, (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
                 (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
-    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st);
+    int homo = 0;
+    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, &homo);
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     if (rc == NREM_OK) {
         cudaEventRecord(t0, st);
-        if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st);
-        else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st);   // samples go to a scratch ring
+        if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st, homo);
+        else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st, homo);   // samples go to a scratch ring
         cudaEventRecord(t1, st);
     }
     cudaError_t e = cudaStreamSynchronize(st);

@@ -33,8 +33,9 @@ __device__ __forceinline__ void normals4f(const Philox4 r, float& z0, float& z1,
     const float m2ln2 = -1.3862943611198906f;          // -2 ln 2
     const float r0 = sqrtaf(m2ln2 * lg2f(u23f(r.x)));
     const float r1 = sqrtaf(m2ln2 * lg2f(u23f(r.z)));
-    const float a0 = two_pi * (u23f(r.y) - 0.5f);
-    const float a1 = two_pi * (u23f(r.w) - 0.5f);
+    // theta = 2 pi (u - 0.5) with u = m - (1 - 2^-24), m = 1.mantissa: one FMA
+    const float a0 = fmaf(__uint_as_float(0x3f800000u | (r.y >> 9)), two_pi, -1.49999994f * two_pi);
+    const float a1 = fmaf(__uint_as_float(0x3f800000u | (r.w >> 9)), two_pi, -1.49999994f * two_pi);
     z0 = r0 * cosaf(a0); z1 = r0 * sinaf(a0);
     z2 = r1 * cosaf(a1); z3 = r1 * sinaf(a1);
 }

@@ -39,6 +39,7 @@ struct BatchArgs {
     const uint64_t* streams;   // [Bs]
     int64_t Bs;
     int tile0;                 // first tile of this launch (tile = tile0 + blockIdx.x)
+    int homo;                  // 1: every map entry is exactly 1 (homogeneous sweep)
     uint32_t step0;            // global Euler step index of the first step of this launch
     int nsteps;
     int init;                  // 1: start from (E0, I0, a_ie_0) instead of loading state
@@ -185,6 +186,12 @@ __global__ void stage_maps_kernel(const double* mapG, const double* mapS, int n_
     const int m = k / kNPad, i = k % kNPad;
     oG[k] = i < N ? (float)mapG[(size_t)m * N + i] : 0.f;
     oS[k] = i < N ? (float)mapS[(size_t)m * N + i] : 0.f;
+}
+// flag[0] &= (every real map entry == 1)
+__global__ void maps_all_ones_kernel(const float* mG, const float* mS, int n_maps, int N, int* flag) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_maps * kNPad) return;
+    if ((k % kNPad) < N && (mG[k] != 1.0f || mS[k] != 1.0f)) flag[0] = 0;
 }
 __global__ void stage_par_kernel(const double* G0, const double* dG, const double* s0, const double* ds,
                                  const uint64_t* streams, int B, int64_t Bs, float* par, uint64_t* st) {
