@@ -46,8 +46,8 @@ struct FiltScratch {
 
 struct FiltRun {
     double s[4], c[4];
-    int64_t k, j;       // position inside the current chunk / chunk index (valid when m >= 16)
-    int64_t kd, jd;     // (m - 15) % ds and (m - 15) / ds
+    int k, j;           // position inside the current chunk / chunk index (valid when m >= 16); all fit in 32 bits
+    int kd, jd;         // (m - 15) % ds and (m - 15) / ds
 };
 
 __device__ __forceinline__ void filt_counters(FiltRun& r, const FiltCoef& f, int64_t m) {
@@ -55,13 +55,13 @@ __device__ __forceinline__ void filt_counters(FiltRun& r, const FiltCoef& f, int
     if (m >= 16) {
         int64_t j = (m - 16) / f.ds;
         if (j > f.J - 1) j = f.J - 1;
-        r.j = j;
-        r.k = m - 16 - j * f.ds;
+        r.j = (int)j;
+        r.k = (int)(m - 16 - j * f.ds);
     } else {
-        r.j = 0; r.k = m - 16;           // negative until m reaches 16
+        r.j = 0; r.k = (int)(m - 16);    // negative until m reaches 16
     }
-    if (m >= 15) { r.jd = (m - 15) / f.ds; r.kd = (m - 15) % f.ds; }
-    else { r.jd = 0; r.kd = m - 15; }
+    if (m >= 15) { r.jd = (int)((m - 15) / f.ds); r.kd = (int)((m - 15) % f.ds); }
+    else { r.jd = 0; r.kd = (int)(m - 15); }
 }
 
 __device__ __forceinline__ void filt_push(FiltRun& r, const FiltCoef& f, const FiltScratch& S, int64_t slot, double u, int64_t m) {
@@ -73,26 +73,28 @@ __device__ __forceinline__ void filt_push(FiltRun& r, const FiltCoef& f, const F
         const double a3 = f.Pr[1] * r.s[3] + f.Pi[1] * r.s[2];
         r.s[0] = a0; r.s[1] = a1; r.s[2] = a2; r.s[3] = a3;
     }
-    if (r.kd == 0 && r.jd < f.J) S.wdec[r.jd * S.nth + slot] = w;
+    const int ds = (int)f.ds, Jm1 = (int)f.J - 1;
+    if (r.kd == 0 && r.jd <= Jm1) S.wdec[(int64_t)r.jd * S.nth + slot] = w;
     if (r.k >= 0) {
         if (r.k == 0) { r.c[0] = r.c[1] = r.c[2] = r.c[3] = 0.0; }
-        const double* pt = f.ptab + 4 * r.k;
-        r.c[0] = fma(__ldg(pt + 0), w, r.c[0]);
-        r.c[1] = fma(__ldg(pt + 1), w, r.c[1]);
-        r.c[2] = fma(__ldg(pt + 2), w, r.c[2]);
-        r.c[3] = fma(__ldg(pt + 3), w, r.c[3]);
-        const bool last_of_chunk = (r.j < f.J - 1) ? (r.k == f.ds - 1) : (m == f.M - 1);
+        const double2* pt = reinterpret_cast<const double2*>(f.ptab) + 2 * r.k;     // the table is 32-byte aligned per row
+        const double2 p01 = __ldg(pt), p23 = __ldg(pt + 1);
+        r.c[0] = fma(p01.x, w, r.c[0]);
+        r.c[1] = fma(p01.y, w, r.c[1]);
+        r.c[2] = fma(p23.x, w, r.c[2]);
+        r.c[3] = fma(p23.y, w, r.c[3]);
+        const bool last_of_chunk = (r.j < Jm1) ? (r.k == ds - 1) : (m == f.M - 1);
         if (last_of_chunk) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) S.summ[(r.j * 4 + q) * S.nth + slot] = r.c[q];
+            for (int q = 0; q < 4; ++q) S.summ[((int64_t)r.j * 4 + q) * S.nth + slot] = r.c[q];
         }
     }
     if (m == f.M - 1) S.wlast[slot] = w;
     // advance the uniform counters
     ++r.k;
-    if (r.k == f.ds && r.j < f.J - 1) { r.k = 0; ++r.j; }
+    if (r.k == ds && r.j < Jm1) { r.k = 0; ++r.j; }
     ++r.kd;
-    if (r.kd == f.ds) { r.kd = 0; ++r.jd; }
+    if (r.kd == ds) { r.kd = 0; ++r.jd; }
 }
 
 // Feeds sample n (index after the cut) with value x; handles both odd extensions.

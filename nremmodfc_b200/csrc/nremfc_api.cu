@@ -96,10 +96,11 @@ static int64_t filt_scratch_doubles(int64_t nth, int64_t J, int64_t ds) {
     return nth * (4 + 4 + 16 + 16 + 5 * J + 1) + (ds + 2 * kPad) * 4;
 }
 
-static FiltScratch carve_filt(double* base, int64_t nth, int64_t J, double** ptab_dev) {
+static FiltScratch carve_filt(double* base, int64_t nth, int64_t J, int64_t ds, double** ptab_dev) {
     FiltScratch S;
     S.nth = nth;
-    double* p = base;
+    *ptab_dev = base;                          // first: keeps the table 32-byte aligned (read as double2)
+    double* p = base + (ds + 2 * kPad) * 4;
     S.fs = p; p += 4 * nth;
     S.cs = p; p += 4 * nth;
     S.head = p; p += 16 * nth;
@@ -107,7 +108,6 @@ static FiltScratch carve_filt(double* base, int64_t nth, int64_t J, double** pta
     S.summ = p; p += 4 * J * nth;
     S.wdec = p; p += J * nth;
     S.wlast = p; p += nth;
-    *ptab_dev = p;
     return S;
 }
 
@@ -204,7 +204,7 @@ int nrem_filtfilt_decimate_f64(const double* bold, int B, int64_t T, int N, int6
     if (int rc = prepare_filter(h_b, h_a, Tf, ds, fh)) return rc;
     const int64_t nth = (int64_t)B * N;
     double* ptab_dev;
-    FiltScratch S = carve_filt((double*)scratch, nth, fh.f.J, &ptab_dev);
+    FiltScratch S = carve_filt((double*)scratch, nth, fh.f.J, ds, &ptab_dev);
     cudaStream_t st = (cudaStream_t)stream;
     NREM_CUDA(cudaMemcpyAsync(ptab_dev, fh.ptab.data(), fh.ptab.size() * 8, cudaMemcpyHostToDevice, st));
     NREM_CUDA(cudaStreamSynchronize(st));       // fh.ptab is pageable host memory owned by this frame
@@ -386,7 +386,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->mapS = (float*)(base + o_ms); P->par = (float*)(base + o_par); P->tile_map = (int32_t*)(base + o_tm);
     P->streams = (uint64_t*)(base + o_st); P->Ebuf = (float*)(base + o_eb); P->bw_state = base + o_bw;
     double* ptab_dev;
-    P->S = carve_filt((double*)(base + o_fs), P->nth, P->J, &ptab_dev);
+    P->S = carve_filt((double*)(base + o_fs), P->nth, P->J, o->bold_downsamp, &ptab_dev);
     P->fh.f.ptab = ptab_dev;
     P->bold_dec = (double*)(base + o_bd); P->fc = (double*)(base + o_fc);
     e = cudaMemcpy(ptab_dev, P->fh.ptab.data(), P->fh.ptab.size() * 8, cudaMemcpyHostToDevice);
@@ -421,7 +421,7 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
     BatchArgs A;
     A.c = make_const(p);
     A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
-    A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp; A.homo = homo;
+    A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp; A.homo = homo; A.zero = 0;
     const int64_t tiles = Bs / kTile;
     int dev = 0, sms = 148;
     NREM_CUDA(cudaGetDevice(&dev));

@@ -40,6 +40,7 @@ struct BatchArgs {
     int64_t Bs;
     int tile0;                 // first tile of this launch (tile = tile0 + blockIdx.x)
     int homo;                  // 1: every map entry is exactly 1 (homogeneous sweep)
+    uint32_t zero;             // always 0: an operand ptxas cannot constant-fold (scheduling ties in wc_tc.cuh)
     uint32_t step0;            // global Euler step index of the first step of this launch
     int nsteps;
     int init;                  // 1: start from (E0, I0, a_ie_0) instead of loading state

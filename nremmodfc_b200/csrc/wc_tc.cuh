@@ -17,6 +17,8 @@
 // tile is [k/4][row] float4 — threads of a warp (consecutive simulations) write consecutive
 // float4, conflict-free.
 #pragma once
+#include <type_traits>
+
 #include "wc_batch.cuh"
 
 namespace nrem {
@@ -140,14 +142,20 @@ constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kB
 // Measured alternatives that LOST on B200 (profiles/r01_kernel_variants.md): an elected issuer warp with a
 // bar.arrive/bar.sync split (+6 %), skipping the padding quads with warp-uniform branches (+37 %: the branches
 // stop the compiler from interleaving quads), 16 or 12 nodes per thread (+2 %).
-// HOMO: homogeneous sweep (every map entry is 1, so G_i and sigma_i are per-simulation scalars: -2 FMA, -2 LDS per
-// node-step).  Constants (-mu, -kA*rhoE) are folded into the FMAs.  Also measured and dropped: drawing the noise of
-// step t+1 inside the E update of step t (+7 %).
-template <int NPASS, int CH, bool HOMO>
+// HOMO : homogeneous sweep (every map entry is 1, so G_i and sigma_i are per-simulation scalars: -2 FMA, -2 LDS per
+//        node-step).  Constants (-mu, -kA*rhoE) are folded into the FMAs.
+// LIGHT: N == 90 only.  The last node chunk (nodes 72..95) holds 18 real nodes and 6 padding nodes; its warps run a
+//        second copy of the step loop compiled for 18 nodes, and the MMA issuer is a thread of that chunk, so the
+//        ~900 clk it spends issuing 36 tcgen05.mma per step are taken from the padding slack instead of making the
+//        other 15 warps wait at the CTA barrier (ncu: 11.7 % of all samples were that wait).
+// PIPE : tie the Philox rounds of quad g+1 behind a MUFU result of quad g (1: the first lg2, 2: the first normal) so
+//        that ptxas cannot hoist all integer work in front of all MUFU work (-2 %).
+template <int NPASS, int CH, bool HOMO, bool LIGHT, int PIPE>
 __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(const BatchArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr bool SPLIT = NPASS == 3;
     constexpr int NT = (kNPad / CH) * kTile;
+    constexpr int NCHUNK = kNPad / CH;
     float* Ah = reinterpret_cast<float*>(smraw);
     float* Al = reinterpret_cast<float*>(smraw + kABytes);
     float* Bh = reinterpret_cast<float*>(smraw + (SPLIT ? 2 : 1) * kABytes);
@@ -165,8 +173,10 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const int64_t sim = (int64_t)tile * kTile + simt;
     const BatchConst& c = A.c;
     const int N = c.N;
+    const bool issuer = tid == 4 * (NCHUNK - 1) * 32;      // first thread of the last chunk
 
     stage_b<NPASS>(A.SCp, Bh, Bl, tid, NT);
+    for (int k = tid; k < (int)(kABytes / 4) * (SPLIT ? 2 : 1); k += NT) Ah[k] = 0.f;     // padding columns of A stay 0
     const int mid = A.tile_map[tile];
     if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
     if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
@@ -199,85 +209,103 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const uint64_t bd_hi = umma_desc(smem_u32(Bh), kLBO_B, kSBO), bd_lo = umma_desc(smem_u32(Bl), kLBO_B, kSBO);
     float4* Ah4 = reinterpret_cast<float4*>(Ah);
     float4* Al4 = reinterpret_cast<float4*>(Al);
-    int rc = A.rec_phase;
-    int64_t row = A.row0;
     const float Pmu = c.P - c.mu;                        // constant part of the E sigmoid argument
     const float nmu = -c.mu, nkr = -A.kA * c.rhoE;
     const float Gh = G0 + dG, sgh = sg0 + dsg;           // HOMO: map == 1 everywhere
-    float xp[CH];
-    // noise (+ constant) term of the E sigmoid argument for one quad of one step
-    auto draw = [&](uint32_t step, int g) {
-        float z[4];
-        normals4f(philox4x32_10(step, (uint32_t)(chunk * (CH / 4) + g), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xp[4 * g + j] = fmaf(c.sq, z[j], Pmu);
-    };
+    const float two_pi = 6.2831853071795865f, m2ln2 = -1.3862943611198906f;
 
-    for (int it = 0; it < A.nsteps; ++it) {
-        // 1. publish E(t) as the A operand
+    // The step loop for a chunk with KN live nodes (KN = CH, or 18 for the last chunk of N = 90).
+    auto run = [&](auto KNc) {
+        constexpr int KN = decltype(KNc)::value;
+        constexpr int NQ = (KN + 3) / 4;
+        int rc = A.rec_phase;
+        int64_t row = A.row0;
+        float xp[CH];
+        for (int it = 0; it < A.nsteps; ++it) {
+            // 1. publish E(t) as the A operand
 #pragma unroll
-        for (int g = 0; g < CH / 4; ++g) {
-            const float4 v = make_float4(E[4 * g], E[4 * g + 1], E[4 * g + 2], E[4 * g + 3]);
-            const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            Ah4[(chunk * (CH / 4) + g) * kTile + simt] = h;
-            if (SPLIT) Al4[(chunk * (CH / 4) + g) * kTile + simt] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        }
-        fence_proxy_async();
-        tc_fence_before();                 // this thread's tcgen05.ld of the previous step precede the barrier
-        __syncthreads();                   // every warp has published its slice and drained its TMEM loads
-        if (tid == 0) {
-            tc_fence_after();
-            issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
-        }
-        // 2. record E(t) (state BEFORE the update, netwWilsonCowanPlastic.py:129-130)
-        if (A.rec) {
-            if (rc == 0) {
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const int node = chunk * CH + k;
-                    if (node < N) A.Ebuf[(row * N + node) * A.Bs + sim] = E[k];
-                }
-                ++row;
+            for (int g = 0; g < NQ; ++g) {
+                const float4 v = make_float4(E[4 * g], E[4 * g + 1], E[4 * g + 2], E[4 * g + 3]);
+                const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+                Ah4[(chunk * (CH / 4) + g) * kTile + simt] = h;
+                if (SPLIT) Al4[(chunk * (CH / 4) + g) * kTile + simt] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
-            if (++rc == A.downsamp) rc = 0;
-        }
-        // 3. everything that does not need the coupling, while the tensor core works
-        const uint32_t step = A.step0 + (uint32_t)it;
+            fence_proxy_async();
+            tc_fence_before();             // this thread's tcgen05.ld of the previous step precede the barrier
+            __syncthreads();               // every warp has published its slice and drained its TMEM loads
+            if (issuer) {
+                tc_fence_after();
+                issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
+            }
+            // 2. record E(t) (state BEFORE the update, netwWilsonCowanPlastic.py:129-130)
+            if (A.rec) {
+                if (rc == 0) {
 #pragma unroll
-        for (int g = 0; g < CH / 4; ++g) {
-            draw(step, g);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 4 * g + j;
+                    for (int k = 0; k < KN; ++k) {
+                        const int node = chunk * CH + k;
+                        if (node < N) A.Ebuf[(row * N + node) * A.Bs + sim] = E[k];
+                    }
+                    ++row;
+                }
+                if (++rc == A.downsamp) rc = 0;
+            }
+            // 3. everything that does not need the coupling, while the tensor core works
+            const uint32_t step = A.step0 + (uint32_t)it;
+            auto node_pre = [&](int k) {
                 xp[k] = fmaf(-a[k], I[k], fmaf(c.a_ee, E[k], xp[k]));
                 const float y = fmaf(-c.a_ii, I[k], fmaf(c.a_ei, E[k], nmu));
                 const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
                 a[k] = fmaf(I[k], fmaf(E[k], A.kA, nkr), a[k]);
                 I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
+            };
+            Philox4 ph = philox4x32_10(step, (uint32_t)(chunk * (CH / 4)), s_lo, s_hi, c.k0, c.k1);
+#pragma unroll
+            for (int g = 0; g < NQ; ++g) {
+                const float l0 = lg2f(u23f(ph.x)), l1 = lg2f(u23f(ph.z));
+                const float a0 = fmaf(__uint_as_float(0x3f800000u | (ph.y >> 9)), two_pi, -1.49999994f * two_pi);
+                const float a1 = fmaf(__uint_as_float(0x3f800000u | (ph.w >> 9)), two_pi, -1.49999994f * two_pi);
+                const float r0 = sqrtaf(m2ln2 * l0), r1 = sqrtaf(m2ln2 * l1);
+                const float z0 = r0 * cosaf(a0);
+                if (g + 1 < NQ) {
+                    // PIPE != 0: A.zero is 0 at run time but opaque to ptxas, so the next quad's counter truly depends on a
+                    // MUFU result of this quad (one LOP3 per quad) and its Philox rounds cannot be hoisted in front of it
+                    const uint32_t ctr = PIPE == 0 ? step : (step ^ (__float_as_uint(PIPE == 1 ? l0 : z0) & A.zero));
+                    ph = philox4x32_10(ctr, (uint32_t)(chunk * (CH / 4) + g + 1), s_lo, s_hi, c.k0, c.k1);
+                }
+                xp[4 * g + 0] = fmaf(c.sq, z0, Pmu);
+                xp[4 * g + 1] = fmaf(c.sq, r0 * sinaf(a0), Pmu);
+                xp[4 * g + 2] = fmaf(c.sq, r1 * cosaf(a1), Pmu);
+                xp[4 * g + 3] = fmaf(c.sq, r1 * sinaf(a1), Pmu);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * g + j < KN) node_pre(4 * g + j);
             }
-        }
-        // 4. coupling -> E(t+1)
-        mbar_wait(bar, (uint32_t)(it & 1));
-        tc_fence_after();
+            // 4. coupling -> E(t+1)
+            mbar_wait(bar, (uint32_t)(it & 1));
+            tc_fence_after();
 #pragma unroll
-        for (int h = 0; h < (CH + 7) / 8; ++h) {
-            uint32_t cr[8];
-            if (8 * h + 8 <= CH) tmem_ld8(tmem_mine + 8 * h, cr); else tmem_ld4(tmem_mine + 8 * h, cr);
-            tmem_ld_wait8(cr);
+            for (int h = 0; h < (KN + 7) / 8; ++h) {
+                uint32_t cr[8];
+                if (8 * h + 8 <= CH) tmem_ld8(tmem_mine + 8 * h, cr); else tmem_ld4(tmem_mine + 8 * h, cr);
+                tmem_ld_wait8(cr);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = 8 * h + j;
-                if (k < CH) {
-                    const int node = chunk * CH + k;
-                    const float Gi = HOMO ? Gh : fmaf(dG, mG[node], G0);
-                    const float sg2 = HOMO ? sgh : fmaf(dsg, mS[node], sg0);
-                    const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);
-                    const float SE = rcpf(1.0f + ex2f(x * sg2));
-                    E[k] = fmaf(c.kE, fmaf(fmaf(-c.rE, E[k], 1.0f), SE, -E[k]), E[k]);
+                for (int j = 0; j < 8; ++j) {
+                    const int k = 8 * h + j;
+                    if (k < KN) {
+                        const int node = chunk * CH + k;
+                        const float Gi = HOMO ? Gh : fmaf(dG, mG[node], G0);
+                        const float sg2 = HOMO ? sgh : fmaf(dsg, mS[node], sg0);
+                        const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);
+                        const float SE = rcpf(1.0f + ex2f(x * sg2));
+                        E[k] = fmaf(c.kE, fmaf(fmaf(-c.rE, E[k], 1.0f), SE, -E[k]), E[k]);
+                    }
                 }
             }
         }
-    }
+    };
+    if (LIGHT && chunk == NCHUNK - 1) run(std::integral_constant<int, 90 - (NCHUNK - 1) * CH>{});
+    else run(std::integral_constant<int, CH>{});
+
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
@@ -292,18 +320,31 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     }
 }
 
-template <int NPASS, int CH, bool HOMO>
+template <int NPASS, bool HOMO, bool LIGHT, int PIPE>
 static int launch_wc_tc_v(const BatchArgs& A, int64_t tiles, cudaStream_t st) {
-    NREM_CUDA(cudaFuncSetAttribute(wc_batch_tc_kernel<NPASS, CH, HOMO>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<NPASS>()));
-    wc_batch_tc_kernel<NPASS, CH, HOMO><<<(unsigned)tiles, (kNPad / CH) * kTile, tc_smem_bytes<NPASS>(), st>>>(A);
+    auto kern = wc_batch_tc_kernel<NPASS, 24, HOMO, LIGHT, PIPE>;
+    NREM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<NPASS>()));
+    kern<<<(unsigned)tiles, (kNPad / 24) * kTile, tc_smem_bytes<NPASS>(), st>>>(A);
     NREM_LAUNCHED();
     return NREM_OK;
 }
 
+// experiment switches (defaults are the measured winners): NREM_TC_PIPE = 0|1|2, NREM_TC_LIGHT = 0|1
+static int g_tc_pipe = []() { const char* e = getenv("NREM_TC_PIPE"); const int v = e ? atoi(e) : 2; return (v >= 0 && v <= 2) ? v : 2; }();
+static int g_tc_light = []() { const char* e = getenv("NREM_TC_LIGHT"); return e ? (atoi(e) != 0) : 1; }();
+
+template <int NPASS, bool HOMO>
+static int launch_wc_tc_h(bool light, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
+    if (NPASS == 3 && g_tc_pipe == 1) return light ? launch_wc_tc_v<NPASS, HOMO, true, 1>(A, tiles, st) : launch_wc_tc_v<NPASS, HOMO, false, 1>(A, tiles, st);
+    if (NPASS == 3 && g_tc_pipe == 2) return light ? launch_wc_tc_v<NPASS, HOMO, true, 2>(A, tiles, st) : launch_wc_tc_v<NPASS, HOMO, false, 2>(A, tiles, st);
+    return light ? launch_wc_tc_v<NPASS, HOMO, true, 0>(A, tiles, st) : launch_wc_tc_v<NPASS, HOMO, false, 0>(A, tiles, st);
+}
+
 // kernel: 2 = TF32, 3 = 3xTF32; homo: every map entry is exactly 1
 static int launch_wc_tc(int kernel, bool homo, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
-    if (kernel == 3) return homo ? launch_wc_tc_v<3, 24, true>(A, tiles, st) : launch_wc_tc_v<3, 24, false>(A, tiles, st);
-    return homo ? launch_wc_tc_v<1, 24, true>(A, tiles, st) : launch_wc_tc_v<1, 24, false>(A, tiles, st);
+    const bool light = g_tc_light && A.c.N == 90;
+    if (kernel == 3) return homo ? launch_wc_tc_h<3, true>(light, A, tiles, st) : launch_wc_tc_h<3, false>(light, A, tiles, st);
+    return homo ? launch_wc_tc_h<1, true>(light, A, tiles, st) : launch_wc_tc_h<1, false>(light, A, tiles, st);
 }
 
 // ---- self-test of the contraction alone --------------------------------------------------------
