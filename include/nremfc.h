@@ -98,6 +98,11 @@ int nrem_fc_f64(const double* bold, int B, int64_t J, int N, double* fc, void* s
 int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, double data_range,
                  double* gof, double* meanfc, void* stream);
 
+/* Replaces utils.kuramoto(BOLD) (utils.py:34-40, whole_sweep_both.py:93): Hilbert phases along time (scipy.signal.hilbert
+ * semantics, length-J FFT), order parameter |mean_n exp(i phase)|, then its mean ("sync") and population std ("meta").
+ *   bold [B,J,N] -> sync_meta [B,2];  scratch_g: device, >= J doubles;  2 <= J <= 1024.                        */
+int nrem_kuramoto_f64(const double* bold, int B, int64_t J, int N, double* sync_meta, void* scratch_g, void* stream);
+
 /* ---- fused sweep (the fast path; no counterpart in the reference) ------------------------- */
 
 /* Per-simulation parameters of a G x sigma x seed x map sweep
@@ -129,7 +134,7 @@ int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan);
 /* Runs the whole pipeline for B simulations.
  *   CM [N,N] f64; mapG,mapS [n_maps,N] f64; G0,dG,sigma0,dsigma [B] f64; h_map_id [B] i32 (HOST pointer, may be NULL = all 0);
  *   streams [B] u64; emp [K,N,N] f64
- *   gof [B,K,4] f64; extra [B,4] f64 = (mean FC, 0, 0, 0) (reserved for sync/meta/peakfreq);
+ *   gof [B,K,4] f64; extra [B,4] f64 = (mean FC, sync, meta, 0) (last slot reserved for peakfreq);
  *   fc NULL or [B,N,N] f64.
  * Returns after the last kernel has been enqueued on `stream`.                                 */
 int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libnremfc.so")
 
 ABI_SYMBOLS = [
     "nrem_abi_version", "nrem_last_error", "nrem_device_count", "nrem_wc_run_f64", "nrem_wc_derivative_f64",
-    "nrem_bold_sim_f64", "nrem_filt_scratch_bytes", "nrem_filtfilt_decimate_f64", "nrem_fc_f64", "nrem_gof_f64",
+    "nrem_bold_sim_f64", "nrem_filt_scratch_bytes", "nrem_filtfilt_decimate_f64", "nrem_fc_f64", "nrem_gof_f64", "nrem_kuramoto_f64",
     "nrem_sweep_create", "nrem_sweep_destroy", "nrem_sweep_device_bytes", "nrem_sweep_run",
     "nrem_sweep_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
 ]
@@ -55,6 +55,7 @@ lib.nrem_filt_scratch_bytes.restype = _i64
 lib.nrem_filt_scratch_bytes.argtypes = [_i, _i64, _i, _i64, _i64]
 lib.nrem_filtfilt_decimate_f64.argtypes = [_vp, _i, _i64, _i, _i64, _i64, C.POINTER(_d), C.POINTER(_d), _vp, _vp, _vp]
 lib.nrem_fc_f64.argtypes = [_vp, _i, _i64, _i, _vp, _vp]
+lib.nrem_kuramoto_f64.argtypes = [_vp, _i, _i64, _i, _vp, _vp, _vp]
 lib.nrem_gof_f64.argtypes = [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]
 lib.nrem_sweep_create.argtypes = [C.POINTER(WCParams), C.POINTER(SweepOpts), _i, _i, _i, C.POINTER(_vp)]
 lib.nrem_sweep_destroy.argtypes = [_vp]

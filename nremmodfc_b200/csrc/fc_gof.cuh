@@ -172,4 +172,38 @@ __global__ void __launch_bounds__(256) gof_f64_kernel(const double* fc, const do
     }
 }
 
+// Kuramoto order parameter of the Hilbert phases (utils.py:34-40: hilbert -> angle -> |mean exp(i angle)| -> mean, std).
+// bold [B][J][N]; g[J] = imag(ifft(h)) is the circular Hilbert kernel of scipy.signal.hilbert for length J, so that
+// imag(analytic)[t] = sum_s g[(t - s) mod J] x[s].  One CTA per simulation, one thread per time point.
+// dynamic smem: (J + 40) doubles.  out [B][2] = (sync, meta).
+__global__ void kuramoto_f64_kernel(const double* bold, const double* g, int J, int N, double* out) {
+    extern __shared__ double smk[];
+    double* gs = smk;
+    double* red = smk + J;
+    const int b = blockIdx.x, t = threadIdx.x;
+    for (int k = t; k < J; k += blockDim.x) gs[k] = g[k];
+    __syncthreads();
+    const double* x = bold + (size_t)b * J * N;
+    double kur = 0.0;
+    if (t < J) {
+        double cr = 0.0, ci = 0.0;
+        for (int n = 0; n < N; ++n) {
+            double im = 0.0;
+            int idx = t;                                   // (t - s) mod J for s = 0
+            for (int s_ = 0; s_ < J; ++s_) {
+                im = fma(gs[idx], x[(size_t)s_ * N + n], im);
+                idx = idx == 0 ? J - 1 : idx - 1;
+            }
+            const double re = x[(size_t)t * N + n];
+            const double mag = sqrt(re * re + im * im);
+            if (mag > 0.0) { cr += re / mag; ci += im / mag; } else { cr += 1.0; }     // np.angle(0) = 0
+        }
+        kur = sqrt(cr * cr + ci * ci) / (double)N;
+    }
+    const double mean = block_sum(t < J ? kur : 0.0, red) / (double)J;
+    const double d = t < J ? kur - mean : 0.0;
+    const double var = block_sum(d * d, red) / (double)J;                              // np.std: population
+    if (t == 0) { out[2 * b] = mean; out[2 * b + 1] = sqrt(var); }
+}
+
 }  // namespace nrem

@@ -238,6 +238,33 @@ int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, doubl
     return NREM_OK;
 }
 
+// Hilbert kernel of scipy.signal.hilbert for length J: h = [1, 2, ..., 2, (1), 0, ...]; g = imag(ifft(h)).
+static std::vector<double> hilbert_kernel(int64_t J) {
+    std::vector<double> g((size_t)J);
+    const long double two_pi = 6.283185307179586476925286766559L;
+    for (int64_t n = 0; n < J; ++n) {
+        long double acc = 0.0L;
+        const int64_t kmax = (J % 2 == 0) ? J / 2 - 1 : (J - 1) / 2;      // bins with weight 2 (k = 0 and J/2 are real)
+        for (int64_t k = 1; k <= kmax; ++k) acc += 2.0L * sinl(two_pi * (long double)((k * n) % J) / (long double)J);
+        g[(size_t)n] = (double)(acc / (long double)J);
+    }
+    return g;
+}
+
+int nrem_kuramoto_f64(const double* bold, int B, int64_t J, int N, double* sync_meta, void* scratch_g, void* stream) {
+    NREM_REQUIRE(bold && sync_meta && scratch_g, "null array");
+    NREM_REQUIRE(B >= 1 && N >= 1, "bad shape");
+    NREM_REQUIRE(J >= 2 && J <= 1024, "kuramoto supports 2 <= J <= 1024 time points");
+    cudaStream_t st = (cudaStream_t)stream;
+    const std::vector<double> g = hilbert_kernel(J);
+    NREM_CUDA(cudaMemcpyAsync(scratch_g, g.data(), sizeof(double) * J, cudaMemcpyHostToDevice, st));
+    NREM_CUDA(cudaStreamSynchronize(st));
+    const int threads = (int)round_up(J, 32);
+    kuramoto_f64_kernel<<<B, threads, sizeof(double) * (J + 40), st>>>(bold, (const double*)scratch_g, (int)J, N, sync_meta);
+    NREM_LAUNCHED();
+    return NREM_OK;
+}
+
 // ---- fused sweep -------------------------------------------------------------------------------
 
 struct nrem_sweep_plan {
@@ -256,6 +283,7 @@ struct nrem_sweep_plan {
     uint64_t* streams;
     void* bw_state;
     double *bold_dec, *fc;
+    double *obs, *hilb;            // [3][B] observables scratch, [J] Hilbert kernel
     // optional timing of the integrator launches (CUDA events on the caller's stream)
     // tile groups: more tiles than SMs are run as independent streams so that the hardware block
     // scheduler keeps every SM busy across chunk boundaries (see integrate())
@@ -378,6 +406,8 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int64_t o_fs = take(8 * filt_scratch_doubles(P->nth, P->J, o->bold_downsamp));
     const int64_t o_bd = take(8 * (int64_t)B * P->J * N);
     const int64_t o_fc = take(8 * (int64_t)B * N * N);
+    const int64_t o_obs = take(8 * 3 * (int64_t)B);
+    const int64_t o_hil = take(8 * std::max<int64_t>(P->J, 1));
     P->dev_bytes = off;
     cudaError_t e = cudaMalloc(&P->dev, (size_t)off);
     if (e != cudaSuccess) { delete P; return fail(NREM_ERR_CUDA, "cudaMalloc(sweep plan): %s%s", cudaGetErrorString(e)); }
@@ -389,6 +419,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->S = carve_filt((double*)(base + o_fs), P->nth, P->J, o->bold_downsamp, &ptab_dev);
     P->fh.f.ptab = ptab_dev;
     P->bold_dec = (double*)(base + o_bd); P->fc = (double*)(base + o_fc);
+    P->obs = (double*)(base + o_obs); P->hilb = (double*)(base + o_hil);
     e = cudaMemcpy(ptab_dev, P->fh.ptab.data(), P->fh.ptab.size() * 8, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(P->dev); delete P; return fail(NREM_ERR_CUDA, "cudaMemcpy(ptab): %s%s", cudaGetErrorString(e)); }
     *plan = P;
@@ -522,8 +553,13 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
     double* meanfc = nullptr;
     if (extra) {
         NREM_CUDA(cudaMemsetAsync(extra, 0, sizeof(double) * 4 * P->B, st));
-        // mean FC goes to extra[b][0]: computed into the plan's scratch then scattered
-        meanfc = P->bold_dec;           // bold_dec is dead after nrem_fc_f64; reuse its first B doubles
+        // sync / meta (utils.kuramoto on the decimated BOLD, whole_sweep_both.py:93) -> plan scratch [B][2]
+        if (P->J <= 1024) {
+            if (int rc = nrem_kuramoto_f64(P->bold_dec, P->B, P->J, N, P->obs, P->hilb, stream)) return rc;
+            NREM_CUDA(cudaMemcpy2DAsync(extra + 1, 4 * sizeof(double), P->obs, 2 * sizeof(double), 2 * sizeof(double), P->B,
+                                        cudaMemcpyDeviceToDevice, st));
+        }
+        meanfc = P->obs + 2 * (int64_t)P->B;         // mean FC -> extra[b][0]
     }
     if (int rc = nrem_gof_f64(fcd, emp, P->B, P->K, N, 1.0, gof, meanfc, stream)) return rc;
     if (extra) {

@@ -215,6 +215,20 @@ def gof(sFC, empFC, data_range=1.0, device=None):
         return d_g.cpu().numpy(), d_m.cpu().numpy()
 
 
+def kuramoto(bold, device=None):
+    """utils.kuramoto (utils.py:34-40) for [J, N] or [B, J, N] -> (sync, meta) per simulation."""
+    dev = _device(device)
+    x, sq = _as_btn(bold, "bold")
+    B, J, N = x.shape
+    with torch.cuda.device(dev):
+        d_in = to_device(x, torch.float64, dev)
+        d_out = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        d_g = torch.empty((J,), dtype=torch.float64, device=dev)
+        check(lib.nrem_kuramoto_f64(_ptr(d_in), B, J, N, _ptr(d_out), _ptr(d_g), _stream()))
+        out = d_out.cpu().numpy()
+    return (float(out[0, 0]), float(out[0, 1])) if sq else (out[:, 0], out[:, 1])
+
+
 KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3}
 
 

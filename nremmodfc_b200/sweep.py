@@ -163,11 +163,12 @@ class SweepPlan:
             d_extra = torch.empty((B, 4), dtype=f64, device=dev)
             d_fc = torch.empty((B, N, N), dtype=f64, device=dev) if want_fc else None
             self.run_device(d_CM, d_mG, d_mS, d_par[0], d_par[1], d_par[2], d_par[3], map_id, d_st, d_emp, d_gof, d_extra, d_fc)
-            out = {"gof": d_gof.cpu().numpy(), "mean": d_extra[:, 0].cpu().numpy()}
+            extra = d_extra.cpu().numpy()
+            out = {"gof": d_gof.cpu().numpy(), "mean": extra[:, 0], "sync": extra[:, 1], "meta": extra[:, 2]}
             if want_fc:
                 out["fc"] = d_fc.cpu().numpy()
         self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in [d_CM, d_mG, d_mS, d_emp, d_st] + d_par)
-        self.d2h_bytes = int(d_gof.numel() * 8 + B * 8 + (d_fc.numel() * 8 if want_fc else 0))
+        self.d2h_bytes = int(d_gof.numel() * 8 + B * 4 * 8 + (d_fc.numel() * 8 if want_fc else 0))
         return out
 
 

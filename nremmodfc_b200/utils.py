@@ -31,12 +31,14 @@ def new_metric(flat1, flat2):
 
 
 def kuramoto(sign):
-    """utils.py:34-40 — Kuramoto order parameter of the Hilbert phases: (mean, std) over time.
-
-    298 x 90 samples per simulation: host-side for now."""
-    analytic = signal.hilbert(np.asarray(sign, dtype=np.float64), axis=0)
-    k = np.abs(np.mean(np.exp(1j * np.angle(analytic)), axis=1))
-    return float(k.mean()), float(k.std())
+    """utils.py:34-40 — Kuramoto order parameter of the Hilbert phases: (mean, std) over time (kuramoto kernel)."""
+    sign = np.asarray(sign, dtype=np.float64)
+    if sign.ndim != 2:
+        raise ValueError("sign must be [time, nodes]")
+    if sign.shape[0] > 1024:                       # longer than the kernel's one-thread-per-time-point layout: SciPy on the host
+        k = np.abs(np.mean(np.exp(1j * np.angle(signal.hilbert(sign, axis=0))), axis=1))
+        return float(k.mean()), float(k.std())
+    return ops.kuramoto(sign)
 
 
 # node groups of the reference (utils.py:52-57)

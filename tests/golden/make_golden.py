@@ -166,3 +166,17 @@ for mod, fn in files.items():
     out[f"{mod}_mean"], out[f"{mod}_sd"], out[f"{mod}_n"] = mean, sd, cnt
     print(mod, "cells", (cnt > 0).sum(), "n range", cnt.min(), cnt.max(), "cell(0,0) eW", mean[5, 10, 8], sd[5, 10, 8])
 save("sweep_cell_stats.npz", cols=np.array(cols), delta_G=dG, delta_sigma=dS, **out)
+
+# ---- 5. HMA known answers (output/emp_15inds_output_16dic.pickle) ------------------------------
+import pickle  # noqa: E402
+
+import HMA as refHMA  # noqa: E402  (the reference's own, pure NumPy)
+
+with open(f"{REF}/output/emp_15inds_output_16dic.pickle", "rb") as fh:
+    emp_out = pickle.load(fh)
+keys = sorted(emp_out.keys())[:: max(1, len(emp_out) // 4)][:4]
+cn = [refHMA.Functional_HP(emp_out[k]["sFC"].copy())[0] for k in keys]       # also pins the module counts per level
+save("hma_kat.npz", sFC=np.stack([emp_out[k]["sFC"] for k in keys]),
+     Hin=np.array([emp_out[k]["Hin_sim"] for k in keys]), Hse=np.array([emp_out[k]["Hse_sim"] for k in keys]),
+     Hin_node=np.stack([emp_out[k]["Hin_node_sim"] for k in keys]), Hse_node=np.stack([emp_out[k]["Hse_node_sim"] for k in keys]),
+     keys=np.array([str(k) for k in keys]), Clus_num=np.array(cn))

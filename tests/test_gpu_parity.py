@@ -272,6 +272,9 @@ def test_sweep_pipeline_vs_oracle(kernel, bold_f32, aal90, oracle_lib):
         g = np.array([bold_oracle.get_all_metrics(out["fc"][k], emp[j]) for j in range(4)])
         assert np.allclose(g, out["gof"][k], atol=1e-9)
         assert abs(out["mean"][k] - out["fc"][k].mean()) < 1e-12
+        sync, meta = bold_oracle.kuramoto(bold_oracle.filt_decimate(oracle_lib.bold_sim(E, 0.04), 10, 100, 0.04))
+        tol = 5e-2 if bold_f32 else 1e-6
+        assert abs(out["sync"][k] - sync) < tol and abs(out["meta"][k] - meta) < tol
 
 
 @pytest.mark.parametrize("passes,tol", [(1, 2e-3), (3, 2e-6)])
@@ -365,3 +368,18 @@ for r in rows: print(repr(r))
         assert all(np.isfinite(row[2:9]))
     # sid is a real seed here: same (seed, cell) would reproduce; different seeds differ
     assert rows[0][2] != rows[2][2]
+
+
+@pytest.mark.parametrize("J,N", [(298, 90), (25, 90), (11, 7), (64, 33)])
+def test_kuramoto_matches_oracle(J, N):
+    """utils.kuramoto (Hilbert phases via a length-J FFT in SciPy) against the direct circular-convolution kernel."""
+    from nremmodfc_b200 import ops, utils
+    from oracle import bold_oracle
+    rng = np.random.default_rng(J)
+    x = np.cumsum(rng.normal(size=(3, J, N)), axis=1) * 1e-4
+    x[2, :, 0] = 0.0                                            # a silent node: np.angle(0) = 0
+    sync, meta = ops.kuramoto(x)
+    for b in range(3):
+        so, mo = bold_oracle.kuramoto(x[b])
+        assert abs(sync[b] - so) < 1e-10 and abs(meta[b] - mo) < 1e-10
+    assert np.allclose(utils.kuramoto(x[0]), bold_oracle.kuramoto(x[0]), atol=1e-10)

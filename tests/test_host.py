@@ -174,10 +174,3 @@ def test_compat_modules_alias_the_package(built):
             "wc.P = 0.123\nassert m.P == 0.123\nprint('ok')\n") % (os.path.join(ROOT, "compat"), ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
-
-
-def test_kuramoto_matches_oracle(built):
-    from nremmodfc_b200 import utils
-    from oracle import bold_oracle
-    x = np.random.default_rng(0).normal(size=(298, 90)).cumsum(axis=0)
-    assert np.allclose(utils.kuramoto(x), bold_oracle.kuramoto(x), rtol=1e-12)
