@@ -38,7 +38,7 @@ def test_euccorr_optima_recovers_planted_minimum(tmp_path):
     tab = {"delta_G": g, "delta_sigma": s}
     for k, st in enumerate(table.STATES):
         target = (dG[5 + k], dS[10 - k])
-        tab[f"e{st}"] = 8 + 40 * ((g - target[0]) ** 2 + (s - target[1]) ** 2) + 0.01 * rng.normal(size=g.size)
+        tab[f"e{st}"] = 8 + 40 * ((g - target[0]) ** 2 + (s - target[1]) ** 2) + 0.002 * rng.normal(size=g.size)
         tab[f"corr{st}"] = np.full(g.size, 0.5)
     opt = table.euccorr_optima(tab)
     for k, st in enumerate(table.STATES):
