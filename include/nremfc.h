@@ -124,6 +124,10 @@ typedef struct nrem_sweep_opts {
     int64_t bold_downsamp;   /* decimation after filtering (reference: 1000)                         */
     double  bold_dt;         /* BOLD Euler step (reference: dt*downsamp = 0.04)                      */
     double  b[5], a[5];      /* band-pass coefficients, SciPy order                                  */
+    int32_t welch_nperseg;   /* 0 = no spectrum; else segment length of signal.welch (reference: 4000; even,   */
+                             /* nperseg/2 = 2^a 5^b <= 2560, multiple of 2*chunk_samples); 50 % overlap, Hann   */
+    int32_t reserved;
+    double  welch_fs;        /* sampling rate of the stored samples, 1/dt (reference: 500 Hz)                 */
 } nrem_sweep_opts;
 
 int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, int n_maps, int K,
@@ -134,7 +138,8 @@ int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan);
 /* Runs the whole pipeline for B simulations.
  *   CM [N,N] f64; mapG,mapS [n_maps,N] f64; G0,dG,sigma0,dsigma [B] f64; h_map_id [B] i32 (HOST pointer, may be NULL = all 0);
  *   streams [B] u64; emp [K,N,N] f64
- *   gof [B,K,4] f64; extra [B,4] f64 = (mean FC, sync, meta, 0) (last slot reserved for peakfreq);
+ *   gof [B,K,4] f64; extra [B,4] f64 = (mean FC, sync, meta, peakfreq) — the last four columns of the reference's
+ *   output row (whole_sweep_both.py:90-96); peakfreq is NaN unless opts.welch_nperseg > 0;
  *   fc NULL or [B,N,N] f64.
  * Returns after the last kernel has been enqueued on `stream`.                                 */
 int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,

@@ -33,7 +33,8 @@ class WCParams(C.Structure):
 class SweepOpts(C.Structure):
     _fields_ = [("kernel", C.c_int32), ("bold_f32", C.c_int32), ("chunk_samples", C.c_int32), ("want_fc", C.c_int32),
                 ("Neq", C.c_int64), ("bold_downsamp", C.c_int64), ("bold_dt", C.c_double),
-                ("b", C.c_double * 5), ("a", C.c_double * 5)]
+                ("b", C.c_double * 5), ("a", C.c_double * 5),
+                ("welch_nperseg", C.c_int32), ("reserved", C.c_int32), ("welch_fs", C.c_double)]
 
 
 if not os.path.exists(LIB_PATH):

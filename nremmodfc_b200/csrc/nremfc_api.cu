@@ -12,6 +12,7 @@
 #include "wc_batch.cuh"
 #include "wc_f64.cuh"
 #include "wc_tc.cuh"
+#include "welch.cuh"
 
 namespace nrem {
 thread_local char g_err[512] = "";
@@ -284,6 +285,12 @@ struct nrem_sweep_plan {
     void* bw_state;
     double *bold_dec, *fc;
     double *obs, *hilb;            // [3][B] observables scratch, [J] Hilbert kernel
+    // Welch spectrum (optional)
+    WelchPlan welch;
+    int64_t ring_rows;             // rows of the E sample buffer (= chunk_samples, or nperseg when the spectrum is on)
+    int welch_nseg;
+    float* welchP;                 // [Bs][nperseg/2 + 1]
+    int welch_smem;
     // optional timing of the integrator launches (CUDA events on the caller's stream)
     // tile groups: more tiles than SMs are run as independent streams so that the hardware block
     // scheduler keeps every SM busy across chunk boundaries (see integrate())
@@ -390,6 +397,27 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->nth = (int64_t)P->N * P->Bs;
     P->chunk_samples = o->chunk_samples > 0 ? o->chunk_samples : 250;
     if (int rc = prepare_filter(o->b, o->a, P->Tf, o->bold_downsamp, P->fh)) { delete P; return rc; }
+    P->ring_rows = P->chunk_samples; P->welch_nseg = 0; P->welchP = nullptr; P->welch.L = 0;
+    std::vector<float> h_win;
+    std::vector<float2> h_tw, h_tw2;
+    if (o->welch_nperseg > 0) {
+        const int L = o->welch_nperseg, M = L / 2;
+        bool ok = (L % 2 == 0) && M <= 2560 && (M % P->chunk_samples == 0) && P->T >= L && o->welch_fs > 0;
+        int m = M, ns = 0;
+        while (ok && m % 4 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 4; m /= 4; }
+        while (ok && m % 2 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 2; m /= 2; }
+        while (ok && m % 5 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 5; m /= 5; }
+        if (!ok || m != 1) { delete P; return fail(NREM_ERR_UNSUPPORTED, "welch: need even nperseg <= T with nperseg/2 = 2^a 5^b <= 2560 and a multiple of chunk_samples%s%s"); }
+        P->welch.L = L; P->welch.M = M; P->welch.nstages = ns;
+        P->ring_rows = L;
+        P->welch_nseg = (int)((P->T - L) / M + 1);
+        P->welch_smem = 2 * kWelchSims * M * 8 + kWelchSims * (M + 1) * 4 + 160;
+        const long double two_pi = 6.283185307179586476925286766559L;
+        h_win.resize(L); h_tw.resize(M); h_tw2.resize(M + 1);
+        for (int n = 0; n < L; ++n) h_win[n] = (float)(0.5L - 0.5L * cosl(two_pi * n / L));          // get_window('hann', L): periodic
+        for (int k = 0; k < M; ++k) h_tw[k] = make_float2((float)cosl(two_pi * k / M), (float)-sinl(two_pi * k / M));
+        for (int k = 0; k <= M; ++k) h_tw2[k] = make_float2((float)cosl(two_pi * k / L), (float)-sinl(two_pi * k / L));
+    }
     // carve one device allocation
     const int N = P->N;
     int64_t off = 0;
@@ -401,13 +429,15 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int64_t o_par = take(4 * 4 * P->Bs);
     const int64_t o_tm = take(4 * P->tiles);
     const int64_t o_st = take(8 * P->Bs);
-    const int64_t o_eb = take(4 * (int64_t)P->chunk_samples * N * P->Bs);
+    const int64_t o_eb = take(4 * P->ring_rows * N * P->Bs);
     const int64_t o_bw = take((o->bold_f32 ? 4 : 8) * 4 * P->nth);
     const int64_t o_fs = take(8 * filt_scratch_doubles(P->nth, P->J, o->bold_downsamp));
     const int64_t o_bd = take(8 * (int64_t)B * P->J * N);
     const int64_t o_fc = take(8 * (int64_t)B * N * N);
     const int64_t o_obs = take(8 * 3 * (int64_t)B);
     const int64_t o_hil = take(8 * std::max<int64_t>(P->J, 1));
+    const int WL = P->welch.L, WM = WL / 2;
+    const int64_t o_wp = take(WL ? 4 * P->Bs * (int64_t)(WM + 1) : 0), o_ww = take(4 * (int64_t)WL), o_wt = take(8 * (int64_t)WM), o_wt2 = take(8 * (int64_t)(WM + 1));
     P->dev_bytes = off;
     cudaError_t e = cudaMalloc(&P->dev, (size_t)off);
     if (e != cudaSuccess) { delete P; return fail(NREM_ERR_CUDA, "cudaMalloc(sweep plan): %s%s", cudaGetErrorString(e)); }
@@ -420,6 +450,15 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->fh.f.ptab = ptab_dev;
     P->bold_dec = (double*)(base + o_bd); P->fc = (double*)(base + o_fc);
     P->obs = (double*)(base + o_obs); P->hilb = (double*)(base + o_hil);
+    if (WL) {
+        P->welchP = (float*)(base + o_wp);
+        P->welch.window = (const float*)(base + o_ww); P->welch.tw = (const float2*)(base + o_wt); P->welch.tw2 = (const float2*)(base + o_wt2);
+        cudaError_t ew = cudaMemcpy(base + o_ww, h_win.data(), 4 * (size_t)WL, cudaMemcpyHostToDevice);
+        if (ew == cudaSuccess) ew = cudaMemcpy(base + o_wt, h_tw.data(), 8 * (size_t)WM, cudaMemcpyHostToDevice);
+        if (ew == cudaSuccess) ew = cudaMemcpy(base + o_wt2, h_tw2.data(), 8 * (size_t)(WM + 1), cudaMemcpyHostToDevice);
+        if (ew == cudaSuccess) ew = cudaFuncSetAttribute(welch_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P->welch_smem);
+        if (ew != cudaSuccess) { cudaFree(P->dev); delete P; return fail(NREM_ERR_CUDA, "welch setup: %s%s", cudaGetErrorString(ew)); }
+    }
     e = cudaMemcpy(ptab_dev, P->fh.ptab.data(), P->fh.ptab.size() * 8, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(P->dev); delete P; return fail(NREM_ERR_CUDA, "cudaMemcpy(ptab): %s%s", cudaGetErrorString(e)); }
     *plan = P;
@@ -485,8 +524,10 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
             A.rec = (ph == 2); A.rec_phase = 0;        // chunks start on a multiple of downsamp
             const int64_t row_base = i0 / p.downsamp;
             const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
+            const int64_t ring = plan ? plan->ring_rows : chunk_samples;
+            const int64_t ring_row0 = row_base % ring;
             if (Ebuf_all) { A.Ebuf = Ebuf_all; A.row0 = row_base; }
-            else { A.Ebuf = d.Ebuf; A.row0 = 0; }
+            else { A.Ebuf = d.Ebuf; A.row0 = ring_row0; }
             for (int g = 0; g < ngroups; ++g) {
                 const int64_t t0 = tiles * g / ngroups, t1 = tiles * (g + 1) / ngroups;
                 A.tile0 = (int)t0;
@@ -506,13 +547,23 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
                 if (ph == 2 && plan) {
                     const int64_t sim0 = t0 * kTile, nsim = (t1 - t0) * kTile;
                     const unsigned blocks = (unsigned)((plan->N * nsim + 127) / 128);
+                    const float* Echunk = d.Ebuf + ring_row0 * (int64_t)plan->N * Bs;
                     if (plan->o.bold_f32)
-                        bold_filter_chunk_kernel<float><<<blocks, 128, 0, gs[g]>>>(d.Ebuf, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
+                        bold_filter_chunk_kernel<float><<<blocks, 128, 0, gs[g]>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
                                                                                 (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S);
                     else
-                        bold_filter_chunk_kernel<double><<<blocks, 128, 0, gs[g]>>>(d.Ebuf, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
+                        bold_filter_chunk_kernel<double><<<blocks, 128, 0, gs[g]>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
                                                                                  plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S);
                     NREM_LAUNCHED();
+                    // Welch: a segment [e - L, e) is complete whenever e >= L and (e - L) is a multiple of the hop L/2
+                    const int64_t e_row = row_base + rows;
+                    if (plan->welch.L > 0 && e_row >= plan->welch.L && (e_row - plan->welch.L) % plan->welch.M == 0) {
+                        const double wsum2 = 0.375 * plan->welch.L;             // sum of a periodic Hann window squared
+                        const float scale = (float)(1.0 / (plan->o.welch_fs * wsum2) / plan->welch_nseg / plan->N);
+                        welch_segment_kernel<<<(unsigned)((nsim + kWelchSims - 1) / kWelchSims), kWelchThreads, plan->welch_smem, gs[g]>>>(
+                            d.Ebuf, plan->ring_rows, (e_row - plan->welch.L) % plan->ring_rows, plan->N, Bs, sim0, nsim, plan->welch, plan->welchP, scale);
+                        NREM_LAUNCHED();
+                    }
                 }
             }
             step += n;
@@ -541,6 +592,7 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
         P->ev_used = 2;
         NREM_CUDA(cudaEventRecord(P->ev[0], st));
     }
+    if (P->welchP) NREM_CUDA(cudaMemsetAsync(P->welchP, 0, 4 * P->Bs * (size_t)(P->welch.M + 1), st));
     int homo = 0;
     if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, &homo)) return rc;
     if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st, homo)) return rc;
@@ -558,6 +610,15 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
             if (int rc = nrem_kuramoto_f64(P->bold_dec, P->B, P->J, N, P->obs, P->hilb, stream)) return rc;
             NREM_CUDA(cudaMemcpy2DAsync(extra + 1, 4 * sizeof(double), P->obs, 2 * sizeof(double), 2 * sizeof(double), P->B,
                                         cudaMemcpyDeviceToDevice, st));
+        }
+        if (P->welchP) {
+            welch_peak_kernel<<<P->B, 256, 0, st>>>(P->welchP, P->welch.M + 1, P->o.welch_fs / P->welch.L, extra + 3, 4);
+            NREM_LAUNCHED();
+        } else {
+            const double nan_v = __builtin_nan("");
+            std::vector<double> nanv((size_t)P->B, nan_v);
+            NREM_CUDA(cudaMemcpy2DAsync(extra + 3, 4 * sizeof(double), nanv.data(), sizeof(double), sizeof(double), P->B, cudaMemcpyHostToDevice, st));
+            NREM_CUDA(cudaStreamSynchronize(st));
         }
         meanfc = P->obs + 2 * (int64_t)P->B;         // mean FC -> extra[b][0]
     }

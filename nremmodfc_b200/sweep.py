@@ -93,7 +93,7 @@ class SweepPlan:
     """Owns the device scratch of one batch size; reusable across calls of ``run``."""
 
     def __init__(self, p, B, n_maps=1, K=4, kernel="auto", bold_f32=True, chunk_samples=0, Neq=2000, bold_downsamp=1000,
-                 bold_dt=None, dt=0.002, device=None):
+                 bold_dt=None, dt=0.002, peakfreq=False, welch_nperseg=4000, device=None):
         self.dev = ops._device(device)
         self.p, self.B, self.n_maps, self.K, self.N = p, int(B), int(n_maps), int(K), p.nnodes
         if bold_dt is None:
@@ -102,6 +102,8 @@ class SweepPlan:
         o = SweepOpts()
         o.kernel, o.bold_f32, o.chunk_samples, o.want_fc = ops.KERNELS[kernel], int(bool(bold_f32)), int(chunk_samples), 0
         o.Neq, o.bold_downsamp, o.bold_dt = int(Neq), int(bold_downsamp), float(bold_dt)
+        # peakfreq: Welch spectrum of the stored E samples (whole_sweep_both.py:90-95: fs = 1/dt, nperseg = 4000)
+        o.welch_nperseg, o.welch_fs = (int(welch_nperseg) if peakfreq else 0), 1.0 / (p.dtSim * p.downsamp)
         o.b = (C.c_double * 5)(*b)
         o.a = (C.c_double * 5)(*a)
         self.opts = o
@@ -164,7 +166,7 @@ class SweepPlan:
             d_fc = torch.empty((B, N, N), dtype=f64, device=dev) if want_fc else None
             self.run_device(d_CM, d_mG, d_mS, d_par[0], d_par[1], d_par[2], d_par[3], map_id, d_st, d_emp, d_gof, d_extra, d_fc)
             extra = d_extra.cpu().numpy()
-            out = {"gof": d_gof.cpu().numpy(), "mean": extra[:, 0], "sync": extra[:, 1], "meta": extra[:, 2]}
+            out = {"gof": d_gof.cpu().numpy(), "mean": extra[:, 0], "sync": extra[:, 1], "meta": extra[:, 2], "peakfreq": extra[:, 3]}
             if want_fc:
                 out["fc"] = d_fc.cpu().numpy()
         self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in [d_CM, d_mG, d_mS, d_emp, d_st] + d_par)

@@ -382,3 +382,26 @@ def test_kuramoto_matches_oracle(J, N):
         so, mo = bold_oracle.kuramoto(x[b])
         assert abs(sync[b] - so) < 1e-10 and abs(meta[b] - mo) < 1e-10
     assert np.allclose(utils.kuramoto(x[0]), bold_oracle.kuramoto(x[0]), atol=1e-10)
+
+
+def test_welch_peak_frequency_matches_scipy(aal90):
+    """peakfreq column (whole_sweep_both.py:90-95): Welch spectrum with SciPy's defaults on the stored E samples.
+    8000 stored samples -> 3 overlapping 4000-sample segments; the oracle runs scipy.signal.welch on the very samples
+    the integrator produced (float32), so the arg-max must agree exactly."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle
+    n1, n2, n3 = 1000, 20000, 160000
+    p = ops.make_params(90, n1, n2, n3, P=0.4, rhoE=0.18, seed=21)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    B = 133
+    dG = np.linspace(-0.1, 0.3, B)
+    streams = np.arange(B, dtype=np.uint64) + 77
+    G0, s0, ds = np.full(B, 0.16), np.full(B, 7.68), np.zeros(B)
+    out = sweep.sweep_gof(p, aal90["SC"], emp, G0, dG, s0, ds, streams, Neq=2000, bold_downsamp=100, peakfreq=True)
+    assert np.isfinite(out["peakfreq"]).all()
+    Eg, _ = ops.integrate_f32(p, aal90["SC"], G0, dG, s0, ds, streams=streams)
+    for k in (0, 40, 127, 128, 132):
+        assert out["peakfreq"][k] == bold_oracle.welch_peak(Eg[:, :, k].astype(np.float64))
+    out2 = sweep.sweep_gof(p, aal90["SC"], emp, G0[:5], dG[:5], s0[:5], ds[:5], streams[:5], Neq=2000, bold_downsamp=100)
+    assert np.isnan(out2["peakfreq"]).all()                     # spectrum not requested
+    assert np.array_equal(out2["gof"], out["gof"][:5])
