@@ -167,7 +167,7 @@ def run_ours(args):
     scale = args.horizon_scale
     pf = ops.make_params(90, int(FULL["n1"] * scale), int(FULL["n2"] * scale), int(FULL["n3"] * scale), P=0.4, rhoE=0.18, seed=2024)
     pw = ops.make_params(90, 200, 40_000, 60_000, P=0.4, rhoE=0.18, seed=2024)     # warm-up pass: 1 % of the horizon
-    plan = sweep.SweepPlan(pf, B, kernel=args.kernel, bold_f32=not args.bold_f64, chunk_samples=args.chunk_samples)
+    plan = sweep.SweepPlan(pf, B, kernel=args.kernel, bold_f32=not args.bold_f64, chunk_samples=args.chunk_samples, peakfreq=args.peakfreq)
     warm = sweep.SweepPlan(pw, B, kernel=args.kernel, bold_f32=not args.bold_f64, chunk_samples=args.chunk_samples, bold_downsamp=100)
     fma_peak, _ = ops.measure_fma_peak()
 
@@ -224,7 +224,7 @@ def run_ours(args):
             "config": {"workload": "configs[1]: homogeneous G x sigma sweep x 50 seeds = 20000 sims per GPU (AAL90 SC, "
                                    "G0=0.16, sigma0=7.68, 1+400+600 s, GoF vs W/N1/N2/N3)",
                        "sims_per_gpu": B, "euler_steps_per_sim": int(STEPS_PER_SIM * scale), "kernel": args.kernel,
-                       "bold_state": "f64" if args.bold_f64 else "f32", "horizon_scale": scale,
+                       "bold_state": "f64" if args.bold_f64 else "f32", "horizon_scale": scale, "peakfreq_column": bool(args.peakfreq),
                        "warmup_pass": "same batch, 1% of the horizon", "l2": "inputs are register/SMEM resident; each step streams "
                        "its own E samples (> L2) through HBM", "results_finite": ok},
             "e2e": {"value": e2e, "unit": "sims/s", "h2d_bytes_per_step": plan.h2d_bytes, "d2h_bytes_per_step": plan.d2h_bytes},
@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--sims", type=int, default=20000, help="simulations per GPU (default: the full 50 x 20 x 20 sweep)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "fma", "tc", "tc3"])
     ap.add_argument("--bold-f64", action="store_true")
+    ap.add_argument("--peakfreq", action="store_true", help="also compute the Welch peak frequency column (whole_sweep_both.py:90-95)")
     ap.add_argument("--chunk-samples", type=int, default=0)
     ap.add_argument("--horizon-scale", type=float, default=1.0, help="DEBUG ONLY: shorten every phase (numbers are then not bench values)")
     ap.add_argument("--cpu-frac", type=float, default=0.05)

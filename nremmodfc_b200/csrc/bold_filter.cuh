@@ -229,7 +229,7 @@ __global__ void filt_backward_kernel(FiltCoef f, FiltScratch S, int64_t nslots, 
 // [sim0, sim0 + nsim), advance the Balloon-Windkessel state and the forward filter.  slot = node*Bs + sim.
 template <typename BT>
 __global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t row_base, int N, int64_t Bs, int64_t sim0, int64_t nsim,
-                                         int64_t Neq, BT dt, BT* bw_state /*[4][nth]*/, FiltCoef f, FiltScratch S) {
+                                         int64_t Neq, BT dt, BT* bw_state /*[4][nth]*/, FiltCoef f, FiltScratch S, float* wring, int wL) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)N * nsim) return;
     const int64_t slot = (t / nsim) * Bs + sim0 + (t % nsim);
@@ -243,9 +243,22 @@ __global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t ro
     filt_load(r, f, S, slot, row_base - Neq);
     const float* in = Ebuf + slot;
     const int64_t stride = (int64_t)N * Bs;
+    // optional series-major copy of the samples for the Welch kernel: wring[slot][sample mod wL], 16-byte stores
+    float* wr = wring ? wring + slot * (int64_t)wL : nullptr;
+    const int lead = (int)((4 - (row_base & 3)) & 3), full_end = lead + ((rows - lead) & ~3);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f;
     for (int rr = 0; rr < rows; ++rr) {
         const int64_t ts = row_base + rr;
-        const double y = bw.step((BT)in[rr * stride], dt);
+        const float xe = in[rr * stride];
+        if (wr) {
+            if (rr < lead || rr >= full_end) wr[ts % wL] = xe;
+            else {
+                const int ph = (rr - lead) & 3;
+                if (ph == 0) q0 = xe; else if (ph == 1) q1 = xe; else if (ph == 2) q2 = xe;
+                else *reinterpret_cast<float4*>(wr + (ts - 3) % wL) = make_float4(q0, q1, q2, xe);
+            }
+        }
+        const double y = bw.step((BT)xe, dt);
         if (ts >= Neq && ts - Neq < f.Tf) filt_feed(r, f, S, slot, y, ts - Neq);
     }
     bw_state[slot] = bw.s; bw_state[S.nth + slot] = bw.f; bw_state[2 * S.nth + slot] = bw.v; bw_state[3 * S.nth + slot] = bw.q;

@@ -287,7 +287,8 @@ struct nrem_sweep_plan {
     double *obs, *hilb;            // [3][B] observables scratch, [J] Hilbert kernel
     // Welch spectrum (optional)
     WelchPlan welch;
-    int64_t ring_rows;             // rows of the E sample buffer (= chunk_samples, or nperseg when the spectrum is on)
+    int64_t ring_rows;             // rows of the integrator's row-major E chunk buffer
+    float* wring;                  // [N*Bs][nperseg] series-major sample ring for the spectrum
     int welch_nseg;
     float* welchP;                 // [Bs][nperseg/2 + 1]
     int welch_smem;
@@ -397,7 +398,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->nth = (int64_t)P->N * P->Bs;
     P->chunk_samples = o->chunk_samples > 0 ? o->chunk_samples : 250;
     if (int rc = prepare_filter(o->b, o->a, P->Tf, o->bold_downsamp, P->fh)) { delete P; return rc; }
-    P->ring_rows = P->chunk_samples; P->welch_nseg = 0; P->welchP = nullptr; P->welch.L = 0;
+    P->ring_rows = P->chunk_samples; P->welch_nseg = 0; P->welchP = nullptr; P->welch.L = 0; P->wring = nullptr;
     std::vector<float> h_win;
     std::vector<float2> h_tw, h_tw2;
     if (o->welch_nperseg > 0) {
@@ -409,9 +410,8 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
         while (ok && m % 5 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 5; m /= 5; }
         if (!ok || m != 1) { delete P; return fail(NREM_ERR_UNSUPPORTED, "welch: need even nperseg <= T with nperseg/2 = 2^a 5^b <= 2560 and a multiple of chunk_samples%s%s"); }
         P->welch.L = L; P->welch.M = M; P->welch.nstages = ns;
-        P->ring_rows = L;
         P->welch_nseg = (int)((P->T - L) / M + 1);
-        P->welch_smem = 2 * kWelchSims * M * 8 + kWelchSims * (M + 1) * 4 + 160;
+        P->welch_smem = 2 * kWelchSims * M * 8 + M * 8 + kWelchSims * (M + 1) * 4 + 160;
         const long double two_pi = 6.283185307179586476925286766559L;
         h_win.resize(L); h_tw.resize(M); h_tw2.resize(M + 1);
         for (int n = 0; n < L; ++n) h_win[n] = (float)(0.5L - 0.5L * cosl(two_pi * n / L));          // get_window('hann', L): periodic
@@ -437,6 +437,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int64_t o_obs = take(8 * 3 * (int64_t)B);
     const int64_t o_hil = take(8 * std::max<int64_t>(P->J, 1));
     const int WL = P->welch.L, WM = WL / 2;
+    const int64_t o_wr = take(4 * (int64_t)WL * P->nth);
     const int64_t o_wp = take(WL ? 4 * P->Bs * (int64_t)(WM + 1) : 0), o_ww = take(4 * (int64_t)WL), o_wt = take(8 * (int64_t)WM), o_wt2 = take(8 * (int64_t)(WM + 1));
     P->dev_bytes = off;
     cudaError_t e = cudaMalloc(&P->dev, (size_t)off);
@@ -452,6 +453,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->obs = (double*)(base + o_obs); P->hilb = (double*)(base + o_hil);
     if (WL) {
         P->welchP = (float*)(base + o_wp);
+        P->wring = (float*)(base + o_wr);
         P->welch.window = (const float*)(base + o_ww); P->welch.tw = (const float2*)(base + o_wt); P->welch.tw2 = (const float2*)(base + o_wt2);
         cudaError_t ew = cudaMemcpy(base + o_ww, h_win.data(), 4 * (size_t)WL, cudaMemcpyHostToDevice);
         if (ew == cudaSuccess) ew = cudaMemcpy(base + o_wt, h_tw.data(), 8 * (size_t)WM, cudaMemcpyHostToDevice);
@@ -550,10 +552,10 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
                     const float* Echunk = d.Ebuf + ring_row0 * (int64_t)plan->N * Bs;
                     if (plan->o.bold_f32)
                         bold_filter_chunk_kernel<float><<<blocks, 128, 0, gs[g]>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
-                                                                                (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S);
+                                                                                (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
                     else
                         bold_filter_chunk_kernel<double><<<blocks, 128, 0, gs[g]>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
-                                                                                 plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S);
+                                                                                 plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
                     NREM_LAUNCHED();
                     // Welch: a segment [e - L, e) is complete whenever e >= L and (e - L) is a multiple of the hop L/2
                     const int64_t e_row = row_base + rows;
@@ -561,7 +563,7 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
                         const double wsum2 = 0.375 * plan->welch.L;             // sum of a periodic Hann window squared
                         const float scale = (float)(1.0 / (plan->o.welch_fs * wsum2) / plan->welch_nseg / plan->N);
                         welch_segment_kernel<<<(unsigned)((nsim + kWelchSims - 1) / kWelchSims), kWelchThreads, plan->welch_smem, gs[g]>>>(
-                            d.Ebuf, plan->ring_rows, (e_row - plan->welch.L) % plan->ring_rows, plan->N, Bs, sim0, nsim, plan->welch, plan->welchP, scale);
+                            plan->wring, (int)((e_row - plan->welch.L) % plan->welch.L), plan->N, Bs, sim0, nsim, plan->welch, plan->welchP, scale);
                         NREM_LAUNCHED();
                     }
                 }

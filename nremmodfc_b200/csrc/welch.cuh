@@ -9,7 +9,8 @@
 //     4*4*5*5*5 for the reference), and un-packed to the L/2+1 one-sided bins;
 //   * |X|^2 is accumulated over nodes in shared memory and added once per launch to P[sim][L/2+1] (float32), so the
 //     E samples are read exactly once more and nothing but the accumulator goes back to HBM.
-// The samples come from a ring of `ring_rows` rows laid out [row][node][sim] (the integrator's E buffer).
+// The samples come from a series-major ring  wring[node][sim][sample mod L]  that the BOLD/filter kernel fills while it
+// consumes the integrator's row-major chunk buffer, so every series is one contiguous, coalesced read.
 #pragma once
 #include "common.cuh"
 
@@ -30,11 +31,15 @@ struct WelchPlan {
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// One Stockham pass of radix R over a series of M complex points: in -> out.  p = product of the previous radices.
-template <int R>
-__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, int M, int p, const float2* tw,
+// One Stockham autosort pass of radix R over M complex points: in -> out.  P = product of the previous radices
+// (compile-time when PC > 0, so that i % p becomes a multiply-shift).  tw[k] = exp(-2 pi i k / M) in shared memory.
+template <int R, int PC>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out, int M, int prt, const float2* tw,
                                               int lane, int nlanes) {
+    const int p = PC > 0 ? PC : prt;
     const int t = M / R;
     const int twstep = M / (p * R);
     for (int i = lane; i < t; i += nlanes) {
@@ -44,105 +49,128 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             u[r] = in[i + r * t];
-            if (r > 0) u[r] = cmul(u[r], tw[(r * k * twstep) % M]);
+            if (r > 0) u[r] = cmul(u[r], tw[r * k * twstep]);          // r*k*twstep < M: no wrap
         }
         if (R == 2) {
-            out[j] = make_float2(u[0].x + u[1].x, u[0].y + u[1].y);
-            out[j + p] = make_float2(u[0].x - u[1].x, u[0].y - u[1].y);
+            out[j] = cadd(u[0], u[1]);
+            out[j + p] = csub(u[0], u[1]);
         } else if (R == 4) {
-            const float2 a = make_float2(u[0].x + u[2].x, u[0].y + u[2].y), b = make_float2(u[0].x - u[2].x, u[0].y - u[2].y);
-            const float2 c = make_float2(u[1].x + u[3].x, u[1].y + u[3].y), d = make_float2(u[1].x - u[3].x, u[1].y - u[3].y);
-            out[j] = make_float2(a.x + c.x, a.y + c.y);
+            const float2 a = cadd(u[0], u[2]), b = csub(u[0], u[2]), c = cadd(u[1], u[3]), d = csub(u[1], u[3]);
+            out[j] = cadd(a, c);
             out[j + p] = make_float2(b.x + d.y, b.y - d.x);            // b - i d
-            out[j + 2 * p] = make_float2(a.x - c.x, a.y - c.y);
+            out[j + 2 * p] = csub(a, c);
             out[j + 3 * p] = make_float2(b.x - d.y, b.y + d.x);        // b + i d
-        } else {                                                        // generic small DFT (R = 5)
-#pragma unroll
-            for (int q = 0; q < R; ++q) {
-                float2 acc = u[0];
-#pragma unroll
-                for (int r = 1; r < R; ++r) acc = make_float2(acc.x + cmul(u[r], tw[((q * r) % R) * (M / R)]).x,
-                                                               acc.y + cmul(u[r], tw[((q * r) % R) * (M / R)]).y);
-                out[j + q * p] = acc;
-            }
+        } else {                                                        // radix 5 (forward transform)
+            const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;      // cos(2 pi/5), cos(4 pi/5)
+            const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;       // sin(2 pi/5), sin(4 pi/5)
+            const float2 a1 = cadd(u[1], u[4]), b1 = csub(u[1], u[4]), a2 = cadd(u[2], u[3]), b2 = csub(u[2], u[3]);
+            out[j] = cadd(u[0], cadd(a1, a2));
+            const float2 m1 = make_float2(u[0].x + c1 * a1.x + c2 * a2.x, u[0].y + c1 * a1.y + c2 * a2.y);
+            const float2 m2 = make_float2(u[0].x + c2 * a1.x + c1 * a2.x, u[0].y + c2 * a1.y + c1 * a2.y);
+            const float2 n1 = make_float2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+            const float2 n2 = make_float2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+            // X1 = m1 - i n1, X4 = m1 + i n1, X2 = m2 - i n2, X3 = m2 + i n2   (-i z = (z.y, -z.x))
+            out[j + p] = make_float2(m1.x + n1.y, m1.y - n1.x);
+            out[j + 4 * p] = make_float2(m1.x - n1.y, m1.y + n1.x);
+            out[j + 2 * p] = make_float2(m2.x + n2.y, m2.y - n2.x);
+            out[j + 3 * p] = make_float2(m2.x - n2.y, m2.y + n2.x);
         }
     }
 }
 
-// dynamic smem: 2 * S * M float2 (ping-pong) + S * (M + 1) float (power accumulator) + 40 floats
-__global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const float* Er, int64_t ring_rows, int64_t start_row, int N, int64_t Bs,
-                                                                     int64_t sim0, int64_t nsim, WelchPlan W, float* P, float scale) {
+// FFT of one series in shared memory; returns the buffer holding the result.
+__device__ __forceinline__ float2* fft_series(float2* a, float2* b, const WelchPlan& W, const float2* tw, int lane, int nlanes, bool active) {
+    const int M = W.M;
+    if (M == 2000) {                      // the reference's nperseg = 4000: radices 4,4,5,5,5 with compile-time strides
+        if (active) stockham_pass<4, 1>(a, b, M, 1, tw, lane, nlanes);
+        __syncthreads();
+        if (active) stockham_pass<4, 4>(b, a, M, 4, tw, lane, nlanes);
+        __syncthreads();
+        if (active) stockham_pass<5, 16>(a, b, M, 16, tw, lane, nlanes);
+        __syncthreads();
+        if (active) stockham_pass<5, 80>(b, a, M, 80, tw, lane, nlanes);
+        __syncthreads();
+        if (active) stockham_pass<5, 400>(a, b, M, 400, tw, lane, nlanes);
+        __syncthreads();
+        return b;
+    }
+    int p = 1;
+    for (int st = 0; st < W.nstages; ++st) {
+        const int R = W.radix[st];
+        if (active) {
+            if (R == 4) stockham_pass<4, 0>(a, b, M, p, tw, lane, nlanes);
+            else if (R == 2) stockham_pass<2, 0>(a, b, M, p, tw, lane, nlanes);
+            else stockham_pass<5, 0>(a, b, M, p, tw, lane, nlanes);
+        }
+        p *= R;
+        float2* t = a; a = b; b = t;
+        __syncthreads();
+    }
+    return a;
+}
+
+// Series-major sample ring: wring[(node * Bs + sim) * L + (sample mod L)] (written by the BOLD/filter kernel).
+// dynamic smem: 2 * S * M float2 (ping-pong) + M float2 (twiddles) + S * (M + 1) float (power accumulator) + 40 floats
+__global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const float* wring, int start, int N, int64_t Bs, int64_t sim0,
+                                                                     int64_t nsim, WelchPlan W, float* P, float scale) {
     extern __shared__ __align__(16) unsigned char smw[];
     const int M = W.M, L = W.L;
     float2* buf0 = reinterpret_cast<float2*>(smw);
     float2* buf1 = buf0 + kWelchSims * M;
-    float* pacc = reinterpret_cast<float*>(buf1 + kWelchSims * M);
+    float2* tw = buf1 + kWelchSims * M;
+    float* pacc = reinterpret_cast<float*>(tw + M);
     float* red = pacc + kWelchSims * (M + 1);
     const int tid = threadIdx.x;
+    constexpr int NL = kWelchThreads / kWelchSims;                       // 64 threads (2 warps) per series
+    const int sub = tid / NL, lane = tid % NL;
     const int64_t s_base = sim0 + (int64_t)blockIdx.x * kWelchSims;
     const int ns = (int)min((int64_t)kWelchSims, sim0 + nsim - s_base);
+    const bool active = sub < ns;
     for (int k = tid; k < kWelchSims * (M + 1); k += kWelchThreads) pacc[k] = 0.f;
-    const int sub = tid / (kWelchThreads / kWelchSims), lane = tid % (kWelchThreads / kWelchSims);   // 64 threads per series
-    constexpr int NL = kWelchThreads / kWelchSims;
-    const int64_t row_stride = (int64_t)N * Bs;
+    for (int k = tid; k < M; k += kWelchThreads) tw[k] = W.tw[k];
+    const int half = start / 2;                                          // start is even: pairs never straddle the wrap
     for (int node = 0; node < N; ++node) {
         __syncthreads();
-        // load (packed even/odd), accumulate the segment mean
         float sum = 0.f;
-        if (sub < ns) {
-            const float* src = Er + (int64_t)node * Bs + s_base + sub;
+        if (active) {
+            const float2* src = reinterpret_cast<const float2*>(wring + ((int64_t)node * Bs + s_base + sub) * L);
             for (int n = lane; n < M; n += NL) {
-                const int64_t r0 = (start_row + 2 * n) % ring_rows, r1 = (start_row + 2 * n + 1) % ring_rows;
-                const float a = src[r0 * row_stride], b = src[r1 * row_stride];
-                buf0[sub * M + n] = make_float2(a, b);
-                sum += a + b;
+                int m = n + half;
+                if (m >= M) m -= M;
+                const float2 v = src[m];
+                buf0[sub * M + n] = v;
+                sum += v.x + v.y;
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if ((tid & 31) == 0) red[tid >> 5] = sum;
         __syncthreads();
-        const float mean = (red[2 * sub] + red[2 * sub + 1]) / (float)L;           // 64 threads = 2 warps per series
-        if (sub < ns) {
-            for (int n = lane; n < M; n += NL) {                                    // detrend='constant', Hann window
+        const float mean = (red[2 * sub] + red[2 * sub + 1]) / (float)L;
+        if (active) {
+            const float2* w2 = reinterpret_cast<const float2*>(W.window);
+            for (int n = lane; n < M; n += NL) {                          // detrend='constant', Hann window
                 float2 v = buf0[sub * M + n];
-                v.x = (v.x - mean) * W.window[2 * n];
-                v.y = (v.y - mean) * W.window[2 * n + 1];
-                buf0[sub * M + n] = v;
+                const float2 w = w2[n];
+                buf0[sub * M + n] = make_float2((v.x - mean) * w.x, (v.y - mean) * w.y);
             }
         }
         __syncthreads();
-        // Stockham passes
-        float2* a = buf0 + sub * M;
-        float2* b = buf1 + sub * M;
-        int p = 1;
-        for (int st = 0; st < W.nstages; ++st) {
-            const int R = W.radix[st];
-            if (sub < ns) {
-                if (R == 4) stockham_pass<4>(a, b, M, p, W.tw, lane, NL);
-                else if (R == 2) stockham_pass<2>(a, b, M, p, W.tw, lane, NL);
-                else stockham_pass<5>(a, b, M, p, W.tw, lane, NL);
-            }
-            p *= R;
-            float2* t = a; a = b; b = t;
-            __syncthreads();
-        }
+        const float2* Z = fft_series(buf0 + sub * M, buf1 + sub * M, W, tw, lane, NL, active);
         // un-pack the real FFT: X[k] = (Z[k] + conj(Z[M-k]))/2 - i w^k (Z[k] - conj(Z[M-k]))/2,  w = exp(-2 pi i / L)
-        if (sub < ns) {
+        if (active) {
             for (int k = lane; k <= M; k += NL) {
-                const float2 zk = a[k % M], zm = a[(M - k) % M];
+                const float2 zk = Z[k == M ? 0 : k], zm = Z[k == 0 ? 0 : M - k];
                 const float2 ev = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
                 const float2 od = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
-                const float2 w = W.tw2[k];
-                const float2 t = cmul(w, od);                                       // -i * t = (t.y, -t.x)
+                const float2 t = cmul(W.tw2[k], od);                      // -i * t = (t.y, -t.x)
                 const float xr = ev.x + t.y, xi = ev.y - t.x;
-                const float pw = (xr * xr + xi * xi) * ((k == 0 || k == M) ? 1.0f : 2.0f);
-                pacc[sub * (M + 1) + k] += pw;
+                pacc[sub * (M + 1) + k] += (xr * xr + xi * xi) * ((k == 0 || k == M) ? 1.0f : 2.0f);
             }
         }
     }
     __syncthreads();
-    if (sub < ns) {
+    if (active) {
         float* dst = P + (s_base + sub) * (int64_t)(M + 1);
         for (int k = lane; k <= M; k += NL) dst[k] += pacc[sub * (M + 1) + k] * scale;
     }
