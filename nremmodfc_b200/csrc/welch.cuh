@@ -17,7 +17,7 @@
 namespace nrem {
 
 constexpr int kWelchSims = 4;
-constexpr int kWelchThreads = 256;
+constexpr int kWelchThreads = 1024;        // 256 threads per series: the passes are latency-bound, occupancy is what pays
 constexpr int kWelchMaxStages = 8;
 
 struct WelchPlan {
@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const floa
     float* pacc = reinterpret_cast<float*>(tw + M);
     float* red = pacc + kWelchSims * (M + 1);
     const int tid = threadIdx.x;
-    constexpr int NL = kWelchThreads / kWelchSims;                       // 64 threads (2 warps) per series
+    constexpr int NL = kWelchThreads / kWelchSims;                       // threads per series
+    constexpr int WPS = NL / 32;                                         // warps per series
     const int sub = tid / NL, lane = tid % NL;
     const int64_t s_base = sim0 + (int64_t)blockIdx.x * kWelchSims;
     const int ns = (int)min((int64_t)kWelchSims, sim0 + nsim - s_base);
@@ -146,7 +147,10 @@ __global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const floa
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if ((tid & 31) == 0) red[tid >> 5] = sum;
         __syncthreads();
-        const float mean = (red[2 * sub] + red[2 * sub + 1]) / (float)L;
+        float msum = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPS; ++w) msum += red[sub * WPS + w];
+        const float mean = msum / (float)L;
         if (active) {
             const float2* w2 = reinterpret_cast<const float2*>(W.window);
             for (int n = lane; n < M; n += NL) {                          // detrend='constant', Hann window
