@@ -97,6 +97,33 @@ __device__ __forceinline__ void filt_push(FiltRun& r, const FiltCoef& f, const F
     if (r.kd == ds) { r.kd = 0; ++r.jd; }
 }
 
+// filt_push for samples strictly inside the signal (16 <= n < Tf - 16): no head/tail/end-of-signal checks.
+__device__ __forceinline__ void filt_push_steady(FiltRun& r, const FiltCoef& f, const FiltScratch& S, int64_t slot, double u, int ds, int Jm1) {
+    const double w = f.b0 * u + 2.0 * ((f.Rr[0] * r.s[0] - f.Ri[0] * r.s[1]) + (f.Rr[1] * r.s[2] - f.Ri[1] * r.s[3]));
+    {
+        const double a0 = f.Pr[0] * r.s[0] - f.Pi[0] * r.s[1] + u;
+        const double a1 = f.Pr[0] * r.s[1] + f.Pi[0] * r.s[0];
+        const double a2 = f.Pr[1] * r.s[2] - f.Pi[1] * r.s[3] + u;
+        const double a3 = f.Pr[1] * r.s[3] + f.Pi[1] * r.s[2];
+        r.s[0] = a0; r.s[1] = a1; r.s[2] = a2; r.s[3] = a3;
+    }
+    if (r.kd == 0) S.wdec[(int64_t)r.jd * S.nth + slot] = w;
+    if (r.k == 0) { r.c[0] = r.c[1] = r.c[2] = r.c[3] = 0.0; }
+    const double2* pt = reinterpret_cast<const double2*>(f.ptab) + 2 * r.k;
+    const double2 p01 = __ldg(pt), p23 = __ldg(pt + 1);
+    r.c[0] = fma(p01.x, w, r.c[0]);
+    r.c[1] = fma(p01.y, w, r.c[1]);
+    r.c[2] = fma(p23.x, w, r.c[2]);
+    r.c[3] = fma(p23.y, w, r.c[3]);
+    ++r.k;
+    if (r.k == ds && r.j < Jm1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) S.summ[((int64_t)r.j * 4 + q) * S.nth + slot] = r.c[q];
+        r.k = 0; ++r.j;
+    }
+    if (++r.kd == ds) { r.kd = 0; ++r.jd; }
+}
+
 // Feeds sample n (index after the cut) with value x; handles both odd extensions.
 __device__ __forceinline__ void filt_feed(FiltRun& r, const FiltCoef& f, const FiltScratch& S, int64_t slot, double x, int64_t n) {
     if (n < 16) {
@@ -159,8 +186,8 @@ template <> struct BW<float> {
         const float k1 = 4.3f * 40.3f * E0 * TE, k2 = 25.0f * E0 * TE, k3 = 1.0f, ia = 1.0f / 0.32f;
         const float lg06 = -0.7369655941662062f;          // log2(1 - E0)
         const float iv = rcpf(v);
-        // the output is formed in float64 from the float32 state: (1-q), (1-v) are exact differences
-        const double out = (double)V0 * ((double)k1 * (1.0 - (double)q) + (double)k2 * (1.0 - (double)(q * iv)) + (double)k3 * (1.0 - (double)v));
+        // (1-q), (1-v) are exact float32 differences; the sum is formed in float32 and widened once for the float64 filter
+        const double out = (double)(V0 * fmaf(k1, 1.0f - q, fmaf(k2, 1.0f - q * iv, k3 * (1.0f - v))));
         const float va = ex2f(ia * lg2f(v));
         const float ds = x - kappa * s - gamma * (f - 1.0f);
         const float df = s;
@@ -246,20 +273,30 @@ __global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t ro
     // optional series-major copy of the samples for the Welch kernel: wring[slot][sample mod wL], 16-byte stores
     float* wr = wring ? wring + slot * (int64_t)wL : nullptr;
     const int lead = (int)((4 - (row_base & 3)) & 3), full_end = lead + ((rows - lead) & ~3);
+    int wpos = wr ? (int)(row_base % wL) : 0;                       // ring position of the current sample
     float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+    // whole chunk strictly inside the filtered signal (no cut, no odd extension, not the end)?  -> lean loop
+    const int64_t n0 = row_base - Neq;
+    const bool steady = n0 >= 16 && n0 + rows <= f.Tf - 16;
+    const int ds = (int)f.ds, Jm1 = (int)f.J - 1;
     for (int rr = 0; rr < rows; ++rr) {
-        const int64_t ts = row_base + rr;
         const float xe = in[rr * stride];
         if (wr) {
-            if (rr < lead || rr >= full_end) wr[ts % wL] = xe;
+            if (rr < lead || rr >= full_end) wr[wpos] = xe;
             else {
                 const int ph = (rr - lead) & 3;
                 if (ph == 0) q0 = xe; else if (ph == 1) q1 = xe; else if (ph == 2) q2 = xe;
-                else *reinterpret_cast<float4*>(wr + (ts - 3) % wL) = make_float4(q0, q1, q2, xe);
+                else *reinterpret_cast<float4*>(wr + wpos - 3) = make_float4(q0, q1, q2, xe);
             }
+            if (++wpos == wL) wpos = 0;
         }
         const double y = bw.step((BT)xe, dt);
-        if (ts >= Neq && ts - Neq < f.Tf) filt_feed(r, f, S, slot, y, ts - Neq);
+        if (steady) {
+            filt_push_steady(r, f, S, slot, y, ds, Jm1);
+        } else {
+            const int64_t ts = row_base + rr;
+            if (ts >= Neq && ts - Neq < f.Tf) filt_feed(r, f, S, slot, y, ts - Neq);
+        }
     }
     bw_state[slot] = bw.s; bw_state[S.nth + slot] = bw.f; bw_state[2 * S.nth + slot] = bw.v; bw_state[3 * S.nth + slot] = bw.q;
     filt_store(r, S, slot);

@@ -163,7 +163,16 @@ int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, 
         NREM_CUDA(cudaFuncSetAttribute(wc_run_f64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big));
         wc_run_f64_kernel<true><<<B, threads, sm_big, st>>>(A);
     } else {
+        // SC does not fit shared memory (N > ~150): read a transposed copy from global memory / L2 (coalesced over nodes)
+        double* CMt = nullptr;
+        NREM_CUDA(cudaMallocAsync((void**)&CMt, sizeof(double) * (size_t)N * N, st));
+        transpose_f64_kernel<<<(N * N + 255) / 256, 256, 0, st>>>(CM, N, CMt);
+        NREM_LAUNCHED();
+        A.CM = CMt;
         wc_run_f64_kernel<false><<<B, threads, sm_small, st>>>(A);
+        NREM_LAUNCHED();
+        NREM_CUDA(cudaFreeAsync(CMt, st));
+        return NREM_OK;
     }
     NREM_LAUNCHED();
     return NREM_OK;

@@ -24,7 +24,8 @@ struct WcF64Args {
 
 __device__ __forceinline__ double sigm(double x, double sigma, double mu) { return 1.0 / (1.0 + exp(-(x - mu) * sigma)); }
 
-// dynamic smem: Es[2][N] then (CM_SMEM) CMt[N][N] with CMt[j*N+i] = CM[i][j]
+// dynamic smem: Es[2][N] then (CM_SMEM) CMt[N][N] with CMt[j*N+i] = CM[i][j]; otherwise A.CM already IS the transpose
+// (global memory, coalesced over i)
 template <bool CM_SMEM>
 __global__ void wc_run_f64_kernel(const WcF64Args A) {
     extern __shared__ double sm64[];
@@ -75,8 +76,13 @@ __global__ void wc_run_f64_kernel(const WcF64Args A) {
                     }
                     if (j < N) acc0 = fma(CMt[j * N + i], e[j], acc0);
                 } else {
-                    const double* row = A.CM + (size_t)i * N;
-                    for (int j = 0; j < N; ++j) acc0 = fma(__ldg(row + j), e[j], acc0);
+                    const double* col = A.CM + i;                       // transposed copy: CMt[j*N + i]
+                    int j = 0;
+                    for (; j + 1 < N; j += 2) {
+                        acc0 = fma(__ldg(col + (size_t)j * N), e[j], acc0);
+                        acc1 = fma(__ldg(col + (size_t)(j + 1) * N), e[j + 1], acc1);
+                    }
+                    if (j < N) acc0 = fma(__ldg(col + (size_t)j * N), e[j], acc0);
                 }
                 const double coup = acc0 + acc1;
                 double nz;
@@ -105,6 +111,11 @@ __global__ void wc_run_f64_kernel(const WcF64Args A) {
         double* f = A.fin + (size_t)b * 3 * N + i;
         f[0] = E; f[N] = I; f[2 * N] = a;
     }
+}
+
+__global__ void transpose_f64_kernel(const double* in, int N, double* out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N * N) out[(size_t)(k % N) * N + k / N] = in[k];
 }
 
 __global__ void wc_derivative_f64_kernel(const nrem_wc_params p, const double* CM, const double* X, const double* G,

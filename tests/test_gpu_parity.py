@@ -405,3 +405,28 @@ def test_welch_peak_frequency_matches_scipy(aal90):
     out2 = sweep.sweep_gof(p, aal90["SC"], emp, G0[:5], dG[:5], s0[:5], ds[:5], streams[:5], Neq=2000, bold_downsamp=100)
     assert np.isnan(out2["peakfreq"]).all()                     # spectrum not requested
     assert np.array_equal(out2["gof"], out["gof"][:5])
+
+
+def test_config5_large_connectome_f64_path(oracle_lib):
+    """BASELINE configs[4]: 1000-node random SC (the module's own placeholder distribution, netwWilsonCowanPlastic.py:64,
+    zero diagonal, mean row sum scaled to AAL90's 2.5).  The tcgen05 sweep is limited to N <= 96; the float64 path takes
+    any N <= 1024 (SC streamed transposed from L2), checked here against the oracle on the same Philox streams."""
+    from nremmodfc_b200 import ops
+    from oracle import wc_oracle
+    N = 1000
+    rng = np.random.default_rng(5)
+    SC = rng.uniform(size=(N, N))
+    np.fill_diagonal(SC, 0.0)
+    SC *= 2.5 / SC.sum(axis=1).mean()
+    n1, n2, n3 = 20, 30, 60
+    p = ops.make_params(N, n1, n2, n3, P=0.4, rhoE=0.18, seed=99)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    G = np.stack([np.full(N, 0.16), np.linspace(0.0, 0.4, N), np.full(N, 0.3)])
+    sg = np.stack([np.full(N, 7.68), np.full(N, 7.5), np.linspace(7.4, 7.9, N)])
+    streams = np.array([3, 4, 5], dtype=np.uint64)
+    Y, fin = ops.wc_run(p, SC, G, sg, B=3, streams=streams)
+    assert Y.shape == (3, 3, 3, N)
+    for b in range(3):
+        Yo = oracle_lib.wc_run(SC, G[b], sg[b], n1, n2, n3, seed=99, stream=int(streams[b]), p=po)
+        fo = oracle_lib.wc_run(SC, G[b], sg[b], n1, n2, n3, seed=99, stream=int(streams[b]), p=po, want="final")
+        assert np.max(np.abs(Y[b] - Yo) / np.abs(Yo)) < 1e-9 and np.max(np.abs(fin[b] - fo) / np.abs(fo)) < 1e-9
