@@ -174,3 +174,30 @@ def test_compat_modules_alias_the_package(built):
             "wc.P = 0.123\nassert m.P == 0.123\nprint('ok')\n") % (os.path.join(ROOT, "compat"), ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_c_abi_argument_errors(built):
+    """Bad arguments come back as negative status codes with a message (no exceptions, no CUDA needed)."""
+    import ctypes as C
+    from nremmodfc_b200 import _lib, ops
+    lib = _lib.lib
+    p = ops.make_params(90, 1, 1, 20)
+    one = C.c_void_p(8)                                        # a non-null dummy "device pointer": never dereferenced
+    assert lib.nrem_fc_f64(None, 1, 10, 90, one, None) == -1 and b"null" in lib.nrem_last_error()
+    assert lib.nrem_fc_f64(one, 1, 10, 200, one, None) == -1 and b"N <= 128" in lib.nrem_last_error()
+    assert lib.nrem_gof_f64(one, one, 1, 4, 3, 1.0, one, None, None) == -1
+    assert lib.nrem_bold_sim_f64(one, 0, 10, 90, 0.04, one, None) == -1
+    assert lib.nrem_wc_run_f64(None, one, one, one, None, None, 1, 1, 1, None, one, None) == -1
+    assert lib.nrem_wc_run_f64(C.byref(p), one, one, one, None, one, 3, 5, 1, None, one, None) == -1      # noise_batch not in {1, B}
+    hb = (C.c_double * 5)(1, 0, -2, 0, 1)
+    ha = (C.c_double * 5)(2, 0, 0, 0, 0)
+    assert lib.nrem_filtfilt_decimate_f64(one, 1, 40, 3, 0, 1, hb, ha, one, one, None) == -1 and b"a[0]" in lib.nrem_last_error()
+    ha = (C.c_double * 5)(1, -0.5, 0, 0, 0)                    # real poles: not two complex-conjugate pairs
+    assert lib.nrem_filtfilt_decimate_f64(one, 1, 40, 3, 0, 1, hb, ha, one, one, None) == -3
+    assert lib.nrem_filt_scratch_bytes(1, 40, 3, 20, 1) == -1      # fewer than 32 samples after the cut
+    o = _lib.SweepOpts()
+    plan = C.c_void_p()
+    pp = ops.make_params(200, 1, 1, 20)
+    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"nnodes <= 96" in lib.nrem_last_error()
+    assert lib.nrem_sweep_run(None, *([one] * 7), None, one, one, one, one, None, None) == -1
+    assert lib.nrem_selftest_tc_coupling(one, one, one, 2, 0, 0, 0, 0, 0, None) == -1
