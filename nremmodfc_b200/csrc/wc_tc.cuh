@@ -147,7 +147,8 @@ constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kB
 // LIGHT: N == 90 only.  The last node chunk (nodes 72..95) holds 18 real nodes and 6 padding nodes; its warps run a
 //        second copy of the step loop compiled for 18 nodes, and the MMA issuer is a thread of that chunk, so the
 //        ~900 clk it spends issuing 36 tcgen05.mma per step are taken from the padding slack instead of making the
-//        other 15 warps wait at the CTA barrier (ncu: 11.7 % of all samples were that wait).
+//        other 15 warps wait at the CTA barrier (ncu: 11.7 % of all samples were that wait); the per-step CTA barrier is
+//        split into bar.arrive (workers) / bar.sync (issuer warp).
 // PIPE : tie the Philox rounds of quad g+1 behind a MUFU result of quad g (1: the first lg2, 2: the first normal) so
 //        that ptxas cannot hoist all integer work in front of all MUFU work (-2 %).
 template <int NPASS, int CH, bool HOMO, bool LIGHT, int PIPE>
@@ -232,7 +233,15 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             }
             fence_proxy_async();
             tc_fence_before();             // this thread's tcgen05.ld of the previous step precede the barrier
-            __syncthreads();               // every warp has published its slice and drained its TMEM loads
+            // Every warp has published its slice and drained its TMEM loads.  With LIGHT only the issuer's warp WAITS for
+            // that (it has the 18-node chunk, so it is early anyway); the others just arrive and go on with the
+            // coupling-free work — they meet the result at the MMA-completion mbarrier (-7 % per step).
+            if (LIGHT) {
+                if (warp == 4 * (NCHUNK - 1)) asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
+                else asm volatile("bar.arrive 1, %0;" ::"r"(NT) : "memory");
+            } else {
+                __syncthreads();
+            }
             if (issuer) {
                 tc_fence_after();
                 issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
