@@ -59,7 +59,10 @@ def to_device(x, dtype, dev):
     """Host array -> device tensor through a pinned staging buffer."""
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=dtype).contiguous()
-    h = torch.from_numpy(np.ascontiguousarray(x))
+    a = np.ascontiguousarray(x)
+    if not a.flags.writeable:          # e.g. arrays straight out of np.load(...): torch wants writable memory
+        a = a.copy()
+    h = torch.from_numpy(a)
     if h.dtype != dtype:
         h = h.to(dtype)
     if h.numel() > 0:

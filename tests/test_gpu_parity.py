@@ -430,3 +430,29 @@ def test_config5_large_connectome_f64_path(oracle_lib):
         Yo = oracle_lib.wc_run(SC, G[b], sg[b], n1, n2, n3, seed=99, stream=int(streams[b]), p=po)
         fo = oracle_lib.wc_run(SC, G[b], sg[b], n1, n2, n3, seed=99, stream=int(streams[b]), p=po, want="final")
         assert np.max(np.abs(Y[b] - Yo) / np.abs(Yo)) < 1e-9 and np.max(np.abs(fin[b] - fo) / np.abs(fo)) < 1e-9
+
+
+@pytest.mark.parametrize("N", [96, 68, 30])
+def test_integrator_other_parcellation_sizes(N, oracle_lib):
+    """The sweep takes any connectome with 7 <= N <= 96 nodes (one 96-wide MMA tile); N = 90 merely gets the 18-node
+    loop for its last chunk.  Same check as for AAL90: float32 kernel vs float64 oracle on the same Philox streams."""
+    from nremmodfc_b200 import ops
+    from oracle import wc_oracle
+    rng = np.random.default_rng(N)
+    SC = rng.uniform(size=(N, N)) * (rng.uniform(size=(N, N)) < 0.4)
+    SC = (SC + SC.T) / 2
+    np.fill_diagonal(SC, 0.0)
+    SC *= 2.5 / SC.sum(axis=1).mean()
+    n1, n2, n3 = 40, 80, 160
+    p = ops.make_params(N, n1, n2, n3, P=0.4, rhoE=0.18, seed=4)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    B = 130
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    streams = rng.integers(0, 2 ** 40, B).astype(np.uint64)
+    for kernel in ("auto", "fma"):
+        E, fin = ops.integrate_f32(p, SC, np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams=streams, kernel=kernel)
+        assert E.shape == (8, N, B)
+        for b in (0, 64, 129):
+            Yo, fo = wc_oracle.run(SC, 0.16 + dG[b], 7.68 + ds[b], n1, n2, n3, seed=4, streams=[int(streams[b])], p=po, return_final=True)
+            assert np.max(np.abs(E[:, :, b] - Yo[0, :, 0, :]) / np.abs(Yo[0, :, 0, :])) < 2e-4
+            assert np.max(np.abs(fin[:, :, b] - fo[0]) / np.abs(fo[0])) < 2e-4
