@@ -214,6 +214,18 @@ def run_ours(args):
     else:                # tile groups overlap on the device: charge the integrator with the WHOLE step (lower bound)
         achieved, timing, share = k1_flops / (dev_ms * 1e-3) / 1e12, f"{groups} tile-group streams overlap; whole-step device time charged", None
         flop_per_launch, avg_ms = k1_flops / groups / max(k1_launches, 1), k1_ms / max(k1_launches, 1)
+    # HBM side of the roofline: the integrator's only algorithmic HBM traffic is the E samples it records
+    # (rows x 90 x sims x 4 B per recording launch); ncu (profiles/r01_final_ncu_integrator.md) measured
+    # dram read+write = 1.694e9 B for a 148-tile, 250-row launch whose algorithmic bytes are 1.705e9.
+    tiles_per_launch = (B + 127) // 128 / groups
+    rows_per_launch = (args.chunk_samples or 250)
+    alg_bytes = rows_per_launch * 90 * tiles_per_launch * 128 * 4
+    ncu_traffic = 1.694e9 / 148 * tiles_per_launch
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md)"
     if rank == 0:
         ok = bool(np.isfinite(table).all())
         line = {
@@ -231,11 +243,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "node_seconds_per_s": value * NODE_SECONDS_PER_SIM,
             "roofline": {"bound": "fp32_fma", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak,
-                         "traffic": None, "kernel": "wc_batch_tc_kernel" if args.kernel != "fma" else "wc_batch_v0_kernel",
+                         "traffic": ncu_traffic, "traffic_note": "dram read+write bytes of one recording launch, ncu --set full, "
+                         "profiles/r01_final_ncu_integrator.md, scaled to the tiles of one launch", "kernel": "wc_batch_tc_kernel" if args.kernel != "fma" else "wc_batch_v0_kernel",
                          "algorithmic_flop_per_euler_step": FLOP_PER_STEP, "kernel_share_of_step": share, "timing": timing,
                          "launches_timed": k1_launches, "avg_launch_ms": avg_ms, "algorithmic_flop_per_launch": flop_per_launch,
                          "peak_source": "measured in this run: register-only FFMA chains on all SMs (nrem_measure_fma_peak)",
-                         "note": "the SC.E contraction runs on tcgen05 tensor cores, so the FP32-FMA roof can be exceeded"},
+                         "note": "the SC.E contraction runs on tcgen05 tensor cores, so the FP32-FMA roof can be exceeded",
+                         "hbm": {"algorithmic_bytes_per_recording_launch": alg_bytes, "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
