@@ -431,7 +431,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int N = P->N;
     int64_t off = 0;
     auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
-    const int64_t o_state = take(4 * 3 * (int64_t)N * P->Bs);
+    const int64_t o_state = take(4 * 4 * (int64_t)N * P->Bs);
     const int64_t o_sc = take(4 * kNPad * kNPad);
     const int64_t o_mg = take(4 * (int64_t)n_maps * kNPad);
     const int64_t o_ms = take(4 * (int64_t)n_maps * kNPad);
@@ -687,10 +687,11 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     const int64_t o_par = take(4 * 4 * Bs), o_tm = take(4 * (Bs / kTile)), o_st = take(8 * Bs);
     const int kDummyRows = 64;
     const int64_t o_dummy = take(E_samples ? 256 : 4 * (int64_t)kDummyRows * N * Bs);
+    const int64_t o_st4 = take(4 * 4 * (int64_t)N * Bs);
     void* dev = nullptr;
     NREM_CUDA(cudaMalloc(&dev, (size_t)off));
     char* base = (char*)dev;
-    StagePtrs d{final_state, (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
+    StagePtrs d{(float*)(base + o_st4), (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
                 (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
     int homo = 0;
     int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, &homo);
@@ -701,6 +702,11 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
         if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st, homo);
         else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st, homo);   // samples go to a scratch ring
         cudaEventRecord(t1, st);
+        if (rc == NREM_OK) {
+            const int64_t n = (int64_t)N * Bs;
+            combine_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.state, n, final_state);
+            ++g_launches;
+        }
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == NREM_OK && e == cudaSuccess) { float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1); g_last_integrate_ms = ms; }

@@ -30,7 +30,7 @@ struct BatchConst {
 
 struct BatchArgs {
     BatchConst c;
-    float* state;              // [3][N][Bs]
+    float* state;              // [4][N][Bs]: E, I, a_ie base, a_ie delta (a_ie = base + delta, see wc_tc.cuh)
     const float* SCp;          // [96][96] zero padded
     const float* mapG;         // [n_maps][96]
     const float* mapS;         // [n_maps][96]
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_v0_kernel(const Bat
             else {
                 E[k] = A.state[(0 * (int64_t)N + node) * A.Bs + sim];
                 I[k] = A.state[(1 * (int64_t)N + node) * A.Bs + sim];
-                a[k] = A.state[(2 * (int64_t)N + node) * A.Bs + sim];
+                a[k] = A.state[(2 * (int64_t)N + node) * A.Bs + sim] + A.state[(3 * (int64_t)N + node) * A.Bs + sim];
             }
         } else { E[k] = 0.f; I[k] = 0.f; a[k] = 0.f; }
     }
@@ -170,8 +170,18 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_v0_kernel(const Bat
             A.state[(0 * (int64_t)N + node) * A.Bs + sim] = E[k];
             A.state[(1 * (int64_t)N + node) * A.Bs + sim] = I[k];
             A.state[(2 * (int64_t)N + node) * A.Bs + sim] = a[k];
+            A.state[(3 * (int64_t)N + node) * A.Bs + sim] = 0.f;       // this validation kernel integrates a_ie directly in float32
         }
     }
+}
+
+// final_state [3][N][Bs] = (E, I, a_base + delta) from the 4-component internal state
+__global__ void combine_state_kernel(const float* st4, int64_t n, float* out3) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    out3[k] = st4[k];
+    out3[n + k] = st4[n + k];
+    out3[2 * n + k] = st4[2 * n + k] + st4[3 * n + k];
 }
 
 // ---- host-side staging kernels (float64 API arrays -> padded float32 device layout) ----------
