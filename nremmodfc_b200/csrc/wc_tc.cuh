@@ -84,8 +84,7 @@ constexpr uint32_t kLBO_A = kTcM * 16;              // next 4-column group of A:
 constexpr uint32_t kLBO_B = kTcN * 16;              // next 4-column group of B: 1536 B
 constexpr uint32_t kABytes = (kTcK / 4) * kLBO_A;   // 49152
 constexpr uint32_t kBBytes = (kTcK / 4) * kLBO_B;   // 36864
-constexpr uint32_t kTmemCols = 256;                 // columns 0..95: coupling accumulator D; 128..223: a_ie base values
-constexpr uint32_t kTmemAbase = 128;
+constexpr uint32_t kTmemCols = 128;                 // columns 0..95: coupling accumulator D
 constexpr uint32_t kRecombine = 4096;               // a_base <- a_base + delta at global steps that are multiples of this
 // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9 / 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
@@ -132,20 +131,13 @@ __device__ __forceinline__ bool elect_one() {
     return p != 0;
 }
 
-// store 8 registers to 8 consecutive columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 
 template <int NPASS>
-constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kBBytes) + 2 * kNPad * 4 + 32; }
+constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kBBytes) + 2 * kNPad * 4 + 32 + (int)kABytes; }
 
 // CH = nodes per thread (24, 16 or 12): the CTA has (96/CH) * 4 warps.
 // Measured alternatives that LOST on B200 (profiles/r01_kernel_variants.md): an elected issuer warp with a
@@ -161,8 +153,9 @@ constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kB
 // a_ie : the plasticity increment dtSim/tau_ip * I (E - rhoE) is ~5e-7 per step while a_ie is 2.5..10, i.e. about ONE
 //        float32 ulp: accumulated directly in float32 the homeostatic loop loses the small corrections (measured: the
 //        homogeneous high-G cells of the full sweep drift off the reference's table).  So a_ie = a_base + delta: a_base
-//        sits in spare TMEM columns for the whole launch (read back with tcgen05.ld, 3 loads per step), only the small
-//        delta is integrated in registers, and the two are recombined once per launch.
+//        sits in shared memory ([node/4][sim] float4, one conflict-free LDS.128 per quad and step; keeping it in spare
+//        TMEM columns instead costs 5 % more because tcgen05.wait::ld cannot be hoisted), only the small delta is
+//        integrated in registers, and the two are recombined at global steps that are multiples of kRecombine.
 // PIPE : tie the Philox rounds of quad g+1 behind a MUFU result of quad g (1: the first lg2, 2: the first normal) so
 //        that ptxas cannot hoist all integer work in front of all MUFU work (-2 %).
 template <int NPASS, int CH, bool HOMO, bool LIGHT, int PIPE>
@@ -180,6 +173,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     float* mS = mG + kNPad;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tail + 2 * kNPad * 4);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 2 * kNPad * 4 + 16);
+    float4* Ab4 = reinterpret_cast<float4*>(tail + 2 * kNPad * 4 + 32);      // a_base [node/4][sim]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = warp >> 2;
@@ -202,7 +196,6 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * CH);
-    const uint32_t tmem_ab = tmem_mine + kTmemAbase;
 
     float E[CH], I[CH], a[CH];
 #pragma unroll
@@ -217,21 +210,18 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             }
         } else { E[k] = 0.f; I[k] = 0.f; a[k] = 0.f; }
     }
-    // a_ie = a_base (TMEM) + delta (registers, a[] from here on); both are part of the stored state (components 2, 3), so
+    // a_ie = a_base (shared memory) + delta (registers, a[] from here on); both are part of the stored state (components 2, 3), so
     // that launch boundaries never round: a_base <- a_base + delta happens only at global steps that are multiples of
     // kRecombine, which makes the result independent of how the run is cut into launches
 #pragma unroll
-    for (int h = 0; h < CH / 8; ++h) {
-        uint32_t w8[8];
+    for (int g = 0; g < CH / 4; ++g) {
+        Ab4[(chunk * (CH / 4) + g) * kTile + simt] = make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = 8 * h + j, node = chunk * CH + k;
-            w8[j] = __float_as_uint(a[k]);
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * g + j, node = chunk * CH + k;
             a[k] = (node < N && !A.init) ? A.state[(3 * (int64_t)N + node) * A.Bs + sim] : 0.f;
         }
-        tmem_st8(tmem_ab + 8 * h, w8);
     }
-    tmem_st_wait();
     const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
     const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
     const uint64_t strm = A.streams[sim];
@@ -292,19 +282,17 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             const uint32_t step = A.step0 + (uint32_t)it;
             if ((step & (kRecombine - 1)) == 0 && step != 0) {       // rare: fold delta into a_base
 #pragma unroll
-                for (int h = 0; h < CH / 8; ++h) {
-                    uint32_t w8[8];
-                    tmem_ld8(tmem_ab + 8 * h, w8);
-                    tmem_ld_wait8(w8);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { w8[j] = __float_as_uint(__uint_as_float(w8[j]) + a[8 * h + j]); a[8 * h + j] = 0.f; }
-                    tmem_st8(tmem_ab + 8 * h, w8);
+                for (int g = 0; g < CH / 4; ++g) {
+                    float4 v = Ab4[(chunk * (CH / 4) + g) * kTile + simt];
+                    v.x += a[4 * g]; v.y += a[4 * g + 1]; v.z += a[4 * g + 2]; v.w += a[4 * g + 3];
+                    a[4 * g] = a[4 * g + 1] = a[4 * g + 2] = a[4 * g + 3] = 0.f;
+                    Ab4[(chunk * (CH / 4) + g) * kTile + simt] = v;
                 }
-                tmem_st_wait();
             }
-            uint32_t ab8[8] = {};                                   // a_base of the current pair of quads
+            float4 ab4 = make_float4(0.f, 0.f, 0.f, 0.f);      // a_base of the current quad
             auto node_pre = [&](int k) {
-                xp[k] = fmaf(-__uint_as_float(ab8[k & 7]), I[k], fmaf(-a[k], I[k], fmaf(c.a_ee, E[k], xp[k])));
+                const float abk = (k & 3) == 0 ? ab4.x : (k & 3) == 1 ? ab4.y : (k & 3) == 2 ? ab4.z : ab4.w;
+                xp[k] = fmaf(-abk, I[k], fmaf(-a[k], I[k], fmaf(c.a_ee, E[k], xp[k])));
                 const float y = fmaf(-c.a_ii, I[k], fmaf(c.a_ei, E[k], nmu));
                 const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
                 a[k] = fmaf(I[k], fmaf(E[k], A.kA, nkr), a[k]);
@@ -328,7 +316,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
                 xp[4 * g + 1] = fmaf(c.sq, r0 * sinaf(a0), Pmu);
                 xp[4 * g + 2] = fmaf(c.sq, r1 * cosaf(a1), Pmu);
                 xp[4 * g + 3] = fmaf(c.sq, r1 * sinaf(a1), Pmu);
-                if ((g & 1) == 0) { tmem_ld8(tmem_ab + 4 * g, ab8); tmem_ld_wait8(ab8); }
+                ab4 = Ab4[(chunk * (CH / 4) + g) * kTile + simt];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (4 * g + j < KN) node_pre(4 * g + j);
@@ -361,12 +349,9 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
 
     float abase[CH];
 #pragma unroll
-    for (int h = 0; h < CH / 8; ++h) {
-        uint32_t w8[8];
-        tmem_ld8(tmem_ab + 8 * h, w8);
-        tmem_ld_wait8(w8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) abase[8 * h + j] = __uint_as_float(w8[j]);
+    for (int g = 0; g < CH / 4; ++g) {
+        const float4 v = Ab4[(chunk * (CH / 4) + g) * kTile + simt];
+        abase[4 * g] = v.x; abase[4 * g + 1] = v.y; abase[4 * g + 2] = v.z; abase[4 * g + 3] = v.w;
     }
     tc_fence_before();
     __syncthreads();
