@@ -456,3 +456,23 @@ def test_integrator_other_parcellation_sizes(N, oracle_lib):
             Yo, fo = wc_oracle.run(SC, 0.16 + dG[b], 7.68 + ds[b], n1, n2, n3, seed=4, streams=[int(streams[b])], p=po, return_final=True)
             assert np.max(np.abs(E[:, :, b] - Yo[0, :, 0, :]) / np.abs(Yo[0, :, 0, :])) < 2e-4
             assert np.max(np.abs(fin[:, :, b] - fo[0]) / np.abs(fo[0])) < 2e-4
+
+
+def test_run_many_seeds_schema_and_hma(aal90):
+    """run_many_seeds.py:105-146 on the batched path (shortened horizon): the reference's pickle schema, FCs clipped in
+    place by HMA, and HMA numbers equal to a fresh evaluation of the stored FC."""
+    from nremmodfc_b200 import HMA, many_seeds, ops
+    p = ops.make_params(90, 200, 2000, 30000, P=0.4, rhoE=0.18, seed=3)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    save = many_seeds.run_many_seeds(p, aal90["SC"], emp, aal90["map_ACh"], aal90["map_NA"], modality="map", seeds=range(3),
+                                     Neq=500, bold_downsamp=20)
+    assert sorted(save) == sorted((s, st) for s in range(3) for st in ("W", "N1", "N2", "N3"))
+    for key, rec in save.items():
+        assert set(rec) == {"Hin_sim", "Hse_sim", "Hin_node_sim", "Hse_node_sim", "sFC"}
+        assert rec["sFC"].shape == (90, 90) and rec["sFC"].min() >= 0.0 and rec["Hin_node_sim"].shape == (90,)
+        num, size, _ = HMA.Functional_HP(rec["sFC"].copy())
+        hin, hse = HMA.Balance(rec["sFC"].copy(), num, size)
+        assert abs(hin - rec["Hin_sim"]) < 1e-12 and abs(hse - rec["Hse_sim"]) < 1e-12
+        assert 0 < rec["Hin_sim"] < 1 and rec["Hse_sim"] > 0
+    # different states use different (delta_G, delta_sigma): W and N1 of one seed must differ
+    assert not np.allclose(save[(0, "W")]["sFC"], save[(0, "N1")]["sFC"])
