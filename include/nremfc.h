@@ -161,6 +161,17 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
                              const double* dsigma, const int32_t* h_map_id, const uint64_t* streams, int B,
                              int n_maps, int64_t nrec, float* E_samples, float* final_state, void* stream);
 
+/* Large connectomes (BASELINE configs[4]; netwWilsonCowanPlastic.py:64-68 allows any nnodes): integrates B simulations of
+ * 16 <= nnodes <= 8192 nodes with one launch per Euler step (tcgen05 GEMM of the whole batch with the node update fused
+ * onto the TMEM accumulator, wc_big.cuh).  Same noise stream, a_ie treatment and outputs as nrem_sweep_integrate_f32;
+ * mapG/mapS are ONE optional per-node map each (device [N], NULL = ones).  All arrays are device pointers.
+ * E_samples [nrec, N, Bpad] (may be NULL), final_state [3, N, Bpad], coup_first (may be NULL) receives the coupling
+ * SC.E of the first step [N, Bpad].                                                                              */
+int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG, const double* mapS,
+                           const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                           const uint64_t* streams, int B, int64_t nrec, float* E_samples, float* final_state,
+                           float* coup_first, void* stream);
+
 /* Self-test of the tcgen05 contraction used by kernels 2/3: out[128,96] = E[128,96] x SCp[96,96]^T (float32,
  * device pointers).  passes = 1 (TF32) or 3 (3xTF32).  The shared-memory descriptor fields (bytes) and the
  * instruction descriptor can be overridden for diagnosis; 0 selects the library's own values.             */

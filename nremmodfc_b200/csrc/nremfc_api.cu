@@ -12,6 +12,7 @@
 #include "wc_batch.cuh"
 #include "wc_f64.cuh"
 #include "wc_tc.cuh"
+#include "wc_big.cuh"
 #include "welch.cuh"
 
 namespace nrem {
@@ -714,6 +715,95 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     cudaFree(dev);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(NREM_ERR_CUDA, "integrate: %s%s", cudaGetErrorString(e));
+    return NREM_OK;
+}
+
+// Large-connectome integrator (wc_big.cuh): one launch per Euler step.
+int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG, const double* mapS,
+                           const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                           const uint64_t* streams, int B, int64_t nrec, float* E_samples, float* final_state,
+                           float* coup_first, void* stream) {
+    if (int rc = check_params(p)) return rc;
+    NREM_REQUIRE(CM && G0 && dG && sigma0 && dsigma && streams, "null array");
+    NREM_REQUIRE(B >= 1, "bad shape");
+    NREM_REQUIRE(p->nnodes >= 16 && p->nnodes <= 8192, "the large-connectome path supports 16 <= nnodes <= 8192");
+    NREM_REQUIRE(!E_samples || nrec >= (p->n3 + p->downsamp - 1) / p->downsamp, "nrec too small");
+    NREM_REQUIRE(final_state, "final_state is required");
+    const int k = resolve_kernel(kernel);
+    NREM_REQUIRE(k == 2 || k == 3, "kernel must be auto, tc or tc3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = p->nnodes;
+    const int Kpad = (int)round_up(N, 4 * kBigKS), KG = Kpad / 4, slices = (N + kBigNT - 1) / kBigNT;
+    const int64_t Bs = round_up(B, kTile);
+    const int tiles = (int)(Bs / kTile);
+    const size_t nf4 = (size_t)tiles * KG * kTile;                      // float4 per state plane
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
+    const int64_t o_a0 = take(2 * 16 * (int64_t)nf4), o_a1 = take(2 * 16 * (int64_t)nf4);
+    const int64_t o_i = take(16 * (int64_t)nf4), o_ab = take(16 * (int64_t)nf4), o_ad = take(16 * (int64_t)nf4);
+    const int64_t o_b = take(2 * 16 * (int64_t)slices * KG * kBigNT);
+    const int64_t o_par = take(4 * 4 * Bs), o_st = take(8 * Bs), o_mg = take(4 * Kpad), o_ms = take(4 * Kpad);
+    void* dev = nullptr;
+    NREM_CUDA(cudaMalloc(&dev, (size_t)off));
+    char* base = (char*)dev;
+    int rc = NREM_OK;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    auto body = [&]() -> int {
+        NREM_CUDA(cudaMemsetAsync(dev, 0, (size_t)o_b, st));            // images and state: padding nodes stay zero for ever
+        const size_t nb = (size_t)slices * KG * kBigNT * 4;
+        big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, (float*)(base + o_b));
+        NREM_LAUNCHED();
+        big_stage_maps_kernel<<<(Kpad + 255) / 256, 256, 0, st>>>(mapG, mapS, N, Kpad, (float*)(base + o_mg), (float*)(base + o_ms));
+        NREM_LAUNCHED();
+        stage_par_kernel<<<(unsigned)((Bs + 255) / 256), 256, 0, st>>>(G0, dG, sigma0, dsigma, streams, B, Bs, (float*)(base + o_par),
+                                                                      (uint64_t*)(base + o_st));
+        NREM_LAUNCHED();
+        BigArgs A;
+        A.c = make_const(*p);
+        big_init_kernel<<<(unsigned)((nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)nf4, KG, (float4*)(base + o_a0), nf4, (float4*)(base + o_i),
+                                                                      (float4*)(base + o_ab));
+        NREM_LAUNCHED();
+        float4* img[2] = {(float4*)(base + o_a0), (float4*)(base + o_a1)};
+        A.Bimg = (const float4*)(base + o_b);
+        A.I4 = (float4*)(base + o_i); A.ab4 = (float4*)(base + o_ab); A.ad4 = (float4*)(base + o_ad);
+        A.par = (const float*)(base + o_par); A.streams = (const uint64_t*)(base + o_st);
+        A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
+        A.Bs = Bs; A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
+        A.Ebuf = E_samples;
+        if (k == 3) NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<3>()));
+        else NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<1>()));
+        const dim3 grid((unsigned)slices, (unsigned)tiles);
+        const int64_t total = p->n1 + p->n2 + p->n3;
+        NREM_CUDA(cudaEventRecord(t0, st));
+        for (int64_t s = 0; s < total; ++s) {
+            const int ph = s < p->n1 ? 0 : (s < p->n1 + p->n2 ? 1 : 2);
+            const int64_t it = s - p->n1 - p->n2;
+            A.Acur = img[s & 1]; A.Anext = img[(s + 1) & 1];
+            A.step = (uint32_t)s;
+            A.kA = (float)(p->dtSim / p->tau_ip[ph]);
+            A.recombine = (s != 0 && (s & (int64_t)(kRecombine - 1)) == 0) ? 1 : 0;
+            A.rec = (E_samples && ph == 2 && it % p->downsamp == 0) ? 1 : 0;
+            A.row = A.rec ? it / p->downsamp : 0;
+            A.coup = s == 0 ? coup_first : nullptr;
+            if (k == 3) wc_big_step_kernel<3><<<grid, kBigThreads, big_smem_bytes<3>(), st>>>(A);
+            else wc_big_step_kernel<1><<<grid, kBigThreads, big_smem_bytes<1>(), st>>>(A);
+            NREM_LAUNCHED();
+        }
+        NREM_CUDA(cudaEventRecord(t1, st));
+        const int64_t n = (int64_t)N * Bs;
+        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, Bs, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
+                                                                      (const float*)A.ab4, (const float*)A.ad4, final_state);
+        NREM_LAUNCHED();
+        return NREM_OK;
+    };
+    rc = body();
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == NREM_OK && e == cudaSuccess) { float ms = 0.f; cudaEventElapsedTime(&ms, t0, t1); g_last_integrate_ms = ms; }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(dev);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(NREM_ERR_CUDA, "big integrate: %s%s", cudaGetErrorString(e));
     return NREM_OK;
 }
 

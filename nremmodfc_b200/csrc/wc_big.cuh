@@ -1,0 +1,299 @@
+// Large-connectome integrator (BASELINE configs[4]: N = 1000 nodes, 4096 instances): one launch per Euler step.
+//
+// Replaces wilsonCowan()+run() (netwWilsonCowanPlastic.py:77-137) when the nodes of a simulation no longer fit the
+// registers of one CTA.  Per step the coupling of ALL simulations is one GEMM
+//     D[Bs sims, N nodes] = E[Bs, N] x SC^T[N, N]            (2 Bs N^2 flop: 8.2 GFLOP at Bs = 4096, N = 1000)
+// tiled 128 sims x 256 nodes per CTA: a producer thread streams K-slices of both operands from L2 into a 4-stage
+// shared-memory ring with cp.async.bulk (mbarrier complete_tx), one thread issues tcgen05.mma (kind::tf32, M = 128,
+// N = 256, K = 8; 3xTF32 split as in wc_tc.cuh) into a 128 x 256 FP32 accumulator in TMEM, and the epilogue warps fuse
+// the whole node update (Philox noise, both sigmoids, E/I/a_ie Euler step, recording) onto the accumulator, so the
+// coupling never touches memory.
+//
+// HBM/L2 layout: every operand lives in global memory as the exact shared-memory image the tensor core wants (no-swizzle
+// K-major canonical layout, [k/4][row][4] floats), so a pipeline stage is ONE contiguous bulk copy per operand:
+//   A image  [2 (hi, lo)][tile][KG][128 sims][4]   E(t) split into TF32-exact hi and the residual lo (E = hi + lo exactly);
+//                                                   two such images ping-pong between steps (the epilogue of step t writes
+//                                                   E(t+1) while other CTAs still read E(t))
+//   B image  [2 (hi, lo)][slice][KG][256 nodes][4]  SC rows of the slice's output nodes, staged once
+//   I, a_base, a_delta                               [tile][KG][128][4], updated in place (one owner thread per element)
+// KG = ceil(N/16)*4 four-node groups; padding nodes are zero in every image and are never written.
+#pragma once
+#include "wc_tc.cuh"
+
+namespace nrem {
+
+constexpr int kBigNT = 256;                 // output nodes per CTA (= MMA N)
+constexpr int kBigKS = 4;                   // four-node groups per pipeline stage (16 input nodes, two K = 8 MMAs)
+constexpr int kBigStages = 4;
+constexpr int kBigEpiWarps = 8;
+constexpr int kBigThreads = (2 + kBigEpiWarps) * 32;
+constexpr int kBigCols = kBigNT / (kBigEpiWarps / 4);     // accumulator columns per epilogue warp
+constexpr uint32_t kBigAStage = kBigKS * kTile * 16;     // 8 KB per (hi | lo)
+constexpr uint32_t kBigBStage = kBigKS * kBigNT * 16;    // 16 KB per (hi | lo)
+constexpr uint32_t kBigLBO_A = kTile * 16;
+constexpr uint32_t kBigLBO_B = kBigNT * 16;
+constexpr uint32_t kBigTmemCols = 256;
+constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+
+template <int NPASS>
+constexpr uint32_t big_stage_bytes() { return (NPASS == 3 ? 2u : 1u) * (kBigAStage + kBigBStage); }
+template <int NPASS>
+constexpr int big_smem_bytes() { return (int)(kBigStages * big_stage_bytes<NPASS>()) + 128; }
+
+struct BigArgs {
+    BatchConst c;
+    const float4* Acur;        // E(t) image
+    float4* Anext;             // E(t+1) image
+    const float4* Bimg;
+    float4* I4;
+    float4* ab4;               // a_ie base
+    float4* ad4;               // a_ie delta (a_ie = base + delta, see wc_tc.cuh)
+    const float* par;          // [4][Bs]: G0, dG, sigma0, dsigma
+    const uint64_t* streams;   // [Bs]
+    const float* mapG;         // [4*KG]
+    const float* mapS;
+    int64_t Bs;
+    int tiles, slices, KG;
+    int homo;                  // maps are all ones
+    uint32_t step;             // global Euler step index
+    float kA;                  // dtSim / tau_ip of this phase
+    int recombine;             // fold a_delta into a_base before this step (global steps that are multiples of kRecombine)
+    int rec;                   // store E(t) into Ebuf row `row`
+    int64_t row;
+    float* Ebuf;               // [rows][N][Bs]
+    float* coup;               // optional [N][Bs]: the coupling SC.E(t) of this step (tests)
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct BigGroup {            // state of one thread's 8 nodes (two four-node groups)
+    float4 eh[2], el[2], i[2], b[2], d[2];
+};
+
+template <int NPASS>
+__global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigArgs A) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    constexpr bool SPLIT = NPASS == 3;
+    constexpr uint32_t STAGE = (NPASS == 3 ? 2u : 1u) * (kBigAStage + kBigBStage);
+    constexpr uint32_t OFF_B = (SPLIT ? 2u : 1u) * kBigAStage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + kBigStages * STAGE);
+    uint64_t* empty = full + kBigStages;
+    uint64_t* accum = empty + kBigStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slice = blockIdx.x, tile = blockIdx.y;
+    const int KT = A.KG / kBigKS;
+    const BatchConst& c = A.c;
+    const int N = c.N;
+
+    if (tid == 0) {
+        for (int s = 0; s < kBigStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kBigTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    const size_t plane = (size_t)A.tiles * A.KG * kTile;                 // float4 per (hi | lo) plane of an A image
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer: one contiguous bulk copy per operand and stage ----
+            const char* a_hi = reinterpret_cast<const char*>(A.Acur + (size_t)tile * A.KG * kTile);
+            const char* a_lo = reinterpret_cast<const char*>(A.Acur + plane + (size_t)tile * A.KG * kTile);
+            const char* b_hi = reinterpret_cast<const char*>(A.Bimg + (size_t)slice * A.KG * kBigNT);
+            const char* b_lo = reinterpret_cast<const char*>(A.Bimg + ((size_t)A.slices + slice) * A.KG * kBigNT);
+            const uint32_t base = smem_u32(smraw);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % kBigStages;
+                mbar_wait(empty + s, (uint32_t)(((kt / kBigStages) & 1) ^ 1));
+                mbar_expect_tx(full + s, STAGE);
+                const uint32_t dst = base + (uint32_t)s * STAGE;
+                bulk_g2s(dst, a_hi + (size_t)kt * kBigAStage, kBigAStage, full + s);
+                if (SPLIT) bulk_g2s(dst + kBigAStage, a_lo + (size_t)kt * kBigAStage, kBigAStage, full + s);
+                bulk_g2s(dst + OFF_B, b_hi + (size_t)kt * kBigBStage, kBigBStage, full + s);
+                if (SPLIT) bulk_g2s(dst + OFF_B + kBigBStage, b_lo + (size_t)kt * kBigBStage, kBigBStage, full + s);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer ----
+            const uint32_t base = smem_u32(smraw);
+            uint32_t acc = 0;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % kBigStages;
+                mbar_wait(full + s, (uint32_t)((kt / kBigStages) & 1));
+                tc_fence_after();
+                const uint32_t sa = base + (uint32_t)s * STAGE;
+                const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO);
+                const uint64_t bd_hi = umma_desc(sa + OFF_B, kBigLBO_B, kSBO), bd_lo = umma_desc(sa + OFF_B + kBigBStage, kBigLBO_B, kSBO);
+#pragma unroll
+                for (int k8 = 0; k8 < kBigKS / 2; ++k8) {
+#pragma unroll
+                    for (int pass = 0; pass < NPASS; ++pass) {
+                        const uint64_t a0 = (pass == 1) ? ad_lo : ad_hi;
+                        const uint64_t b0 = (pass == 2) ? bd_lo : bd_hi;
+                        umma_tf32(tmem_d, a0 + (uint64_t)(k8 * ((2 * kBigLBO_A) >> 4)), b0 + (uint64_t)(k8 * ((2 * kBigLBO_B) >> 4)), kBigIdesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(empty + s);        // the stage may be refilled once these MMAs have read it
+            }
+            umma_commit(accum);
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue: the node update of (128 sims) x (256 nodes), fused onto the TMEM accumulator ----
+        const int q = warp & 3;                               // TMEM lane quarter this warp may read
+        const int cgp = (warp - 2) >> 2;                      // column group
+        const int r = q * 32 + lane;
+        const int64_t sim = (int64_t)tile * kTile + r;
+        const uint32_t tmem_mine = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(cgp * kBigCols);
+        const int node_base = slice * kBigNT + cgp * kBigCols;
+        const size_t rowbase = (size_t)tile * A.KG * kTile + r;
+        const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
+        const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
+        const uint64_t strm = A.streams[sim];
+        const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
+        const float Pmu = c.P - c.mu, nmu = -c.mu, nkr = -A.kA * c.rhoE;
+        const float Gh = G0 + dG, sgh = sg0 + dsg;
+        int ng = (N - node_base + 7) / 8;
+        ng = ng < 0 ? 0 : (ng > kBigCols / 8 ? kBigCols / 8 : ng);
+
+        auto load8 = [&](int g, BigGroup& s) {
+            const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                s.eh[h] = A.Acur[idx + h * kTile];
+                s.el[h] = A.Acur[plane + idx + h * kTile];
+                s.i[h] = A.I4[idx + h * kTile];
+                s.b[h] = A.ab4[idx + h * kTile];
+                s.d[h] = A.ad4[idx + h * kTile];
+            }
+        };
+        BigGroup cur, nxt;
+        if (ng > 0) load8(0, cur);
+        mbar_wait(accum, 0);
+        tc_fence_after();
+        for (int g = 0; g < ng; ++g) {
+            if (g + 1 < ng) load8(g + 1, nxt);
+            uint32_t cr[8];
+            tmem_ld8(tmem_mine + 8 * g, cr);
+            tmem_ld_wait8(cr);
+            const int node0 = node_base + 8 * g;
+            const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float z[4];
+                normals4f(philox4x32_10(A.step, (uint32_t)((node0 >> 2) + h), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+                float E[4] = {cur.eh[h].x + cur.el[h].x, cur.eh[h].y + cur.el[h].y, cur.eh[h].z + cur.el[h].z, cur.eh[h].w + cur.el[h].w};
+                float I[4] = {cur.i[h].x, cur.i[h].y, cur.i[h].z, cur.i[h].w};
+                float ab[4] = {cur.b[h].x, cur.b[h].y, cur.b[h].z, cur.b[h].w};
+                float ad[4] = {cur.d[h].x, cur.d[h].y, cur.d[h].z, cur.d[h].w};
+                float hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int node = node0 + 4 * h + j;
+                    const bool live = node < N;
+                    const float coup = __uint_as_float(cr[4 * h + j]);
+                    if (A.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
+                    if (live && A.rec) A.Ebuf[((size_t)A.row * N + node) * A.Bs + sim] = E[j];      // state BEFORE the update (WC:129-130)
+                    if (live && A.coup) A.coup[(size_t)node * A.Bs + sim] = coup;
+                    float xp = fmaf(c.sq, z[j], Pmu);
+                    xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(c.a_ee, E[j], xp)));
+                    const float y = fmaf(-c.a_ii, I[j], fmaf(c.a_ei, E[j], nmu));
+                    const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
+                    const float dn = fmaf(I[j], fmaf(E[j], A.kA, nkr), ad[j]);
+                    const float In = fmaf(c.kI, fmaf(fmaf(-c.rI, I[j], 1.0f), SI, -I[j]), I[j]);
+                    const float Gi = A.homo ? Gh : fmaf(dG, __ldg(A.mapG + node), G0);
+                    const float sg2 = A.homo ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
+                    const float x = fmaf(Gi, coup, xp);
+                    const float SE = rcpf(1.0f + ex2f(x * sg2));
+                    const float En = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
+                    hi[j] = live ? tf32_rn(En) : 0.f;
+                    lo[j] = live ? En - hi[j] : 0.f;
+                    I[j] = live ? In : 0.f;
+                    ad[j] = live ? dn : 0.f;
+                }
+                A.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                A.Anext[plane + idx + h * kTile] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                A.I4[idx + h * kTile] = make_float4(I[0], I[1], I[2], I[3]);
+                A.ad4[idx + h * kTile] = make_float4(ad[0], ad[1], ad[2], ad[3]);
+                if (A.recombine) A.ab4[idx + h * kTile] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+            }
+            cur = nxt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_d, kBigTmemCols);
+}
+
+// ---- staging ---------------------------------------------------------------------------------------------------------
+// SC (float64 [N][N], row = target node) -> B image hi/lo
+__global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, float* Bimg) {
+    const size_t total = (size_t)slices * KG * kBigNT * 4;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int kk = (int)(idx & 3);
+    const int nl = (int)((idx >> 2) % kBigNT);
+    const size_t rest = (idx >> 2) / kBigNT;
+    const int kg = (int)(rest % KG), slice = (int)(rest / KG);
+    const int n = slice * kBigNT + nl, k = kg * 4 + kk;
+    const float v = (n < N && k < N) ? (float)CM[(size_t)n * N + k] : 0.f;
+    const float h = tf32_rn(v);
+    Bimg[idx] = h;
+    Bimg[total + idx] = v - h;
+}
+
+__global__ void big_stage_maps_kernel(const double* mapG, const double* mapS, int N, int Kpad, float* mG, float* mS) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kpad) return;
+    mG[k] = (k < N && mapG) ? (float)mapG[k] : 1.f;
+    mS[k] = (k < N && mapS) ? (float)mapS[k] : 1.f;
+}
+
+// initial condition (netwWilsonCowanPlastic.py:90-99) into the images; every array was zeroed before
+__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, float4* A0, size_t plane, float4* I4, float4* ab4) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index [tile][kg][r]
+    if (idx >= nf4) return;
+    const int kg = (int)((idx / kTile) % KG);
+    float e[4], l[4], i[4], a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool live = kg * 4 + j < c.N;
+        e[j] = live ? tf32_rn(c.E0) : 0.f;
+        l[j] = live ? c.E0 - e[j] : 0.f;
+        i[j] = live ? c.I0 : 0.f;
+        a[j] = live ? c.a0 : 0.f;
+    }
+    A0[idx] = make_float4(e[0], e[1], e[2], e[3]);
+    A0[plane + idx] = make_float4(l[0], l[1], l[2], l[3]);
+    I4[idx] = make_float4(i[0], i[1], i[2], i[3]);
+    ab4[idx] = make_float4(a[0], a[1], a[2], a[3]);
+}
+
+// images -> final state [3][N][Bs] (E, I, a_ie), simulation fastest
+__global__ void big_export_kernel(int N, int KG, int64_t Bs, const float* Aimg, size_t plane_f, const float* I, const float* ab,
+                                  const float* ad, float* fin) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (int64_t)N * Bs) return;
+    const int64_t sim = k % Bs;
+    const int node = (int)(k / Bs);
+    const size_t src = (((size_t)(sim / kTile) * KG + (node >> 2)) * kTile + (size_t)(sim % kTile)) * 4 + (node & 3);
+    fin[k] = Aimg[src] + Aimg[plane_f + src];
+    fin[(int64_t)N * Bs + k] = I[src];
+    fin[2 * (int64_t)N * Bs + k] = ab[src] + ad[src];
+}
+
+}  // namespace nrem

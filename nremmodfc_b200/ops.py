@@ -263,6 +263,38 @@ def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=No
         return E, d_fin[:, :, :B].cpu().numpy()
 
 
+def big_integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, streams=None, kernel="auto", record=True,
+                      want_coupling=False, device=None):
+    """Large-connectome integrator (BASELINE configs[4]; csrc/wc_big.cuh): any 16 <= nnodes <= 8192, one launch per Euler
+    step.  Returns (E samples [nrec, N, B] or None, final [3, N, B]) and, with want_coupling, SC.E of the first step [N, B].
+    `ops.last_integrate_ms()` gives the device time of the step launches."""
+    dev = _device(device)
+    N = p.nnodes
+    G0 = np.atleast_1d(np.asarray(G0, dtype=np.float64))
+    B = G0.shape[0]
+    Bs = (B + 127) // 128 * 128
+    nrec = (p.n3 + p.downsamp - 1) // p.downsamp
+    with torch.cuda.device(dev):
+        d = [to_device(np.broadcast_to(np.asarray(a, dtype=np.float64), (B,)).copy(), torch.float64, dev)
+             for a in (G0, dG, sigma0, dsigma)]
+        d_CM = to_device(np.asarray(CM, dtype=np.float64), torch.float64, dev)
+        if tuple(d_CM.shape) != (N, N):
+            raise ValueError(f"CM must be ({N}, {N})")
+        d_mG = None if mapG is None else to_device(np.asarray(mapG, dtype=np.float64).reshape(N), torch.float64, dev)
+        d_mS = None if mapS is None else to_device(np.asarray(mapS, dtype=np.float64).reshape(N), torch.float64, dev)
+        d_st = _u64(np.arange(B) if streams is None else streams, dev)
+        d_E = torch.empty((max(nrec, 1), N, Bs), dtype=torch.float32, device=dev) if record and nrec > 0 else None
+        d_fin = torch.empty((3, N, Bs), dtype=torch.float32, device=dev)
+        d_cp = torch.empty((N, Bs), dtype=torch.float32, device=dev) if want_coupling else None
+        check(lib.nrem_big_integrate_f32(C.byref(p), KERNELS[kernel], _ptr(d_CM), _ptr(d_mG), _ptr(d_mS), _ptr(d[0]), _ptr(d[1]),
+                                         _ptr(d[2]), _ptr(d[3]), _ptr(d_st), B, nrec, _ptr(d_E), _ptr(d_fin), _ptr(d_cp), _stream()))
+        E = d_E[:, :, :B].cpu().numpy() if d_E is not None else None
+        fin = d_fin[:, :, :B].cpu().numpy()
+        if want_coupling:
+            return E, fin, d_cp[:, :B].cpu().numpy()
+        return E, fin
+
+
 def selftest_tc_coupling(E, SC, passes=1, lboA=0, sboA=0, lboB=0, sboB=0, idesc=0, device=None):
     """out[128, 96] = E[128, 96] @ SC[96, 96].T through the tcgen05 path of the integrator (diagnostic)."""
     dev = _device(device)

@@ -476,3 +476,62 @@ def test_run_many_seeds_schema_and_hma(aal90):
         assert 0 < rec["Hin_sim"] < 1 and rec["Hse_sim"] > 0
     # different states use different (delta_G, delta_sigma): W and N1 of one seed must differ
     assert not np.allclose(save[(0, "W")]["sFC"], save[(0, "N1")]["sFC"])
+
+
+def _random_sc(N, seed):
+    """netwWilsonCowanPlastic.py:64 placeholder distribution, zero diagonal, mean row sum scaled to AAL90's 2.5."""
+    rng = np.random.default_rng(seed)
+    SC = rng.uniform(size=(N, N))
+    np.fill_diagonal(SC, 0.0)
+    return SC * (2.5 / SC.sum(axis=1).mean())
+
+
+@pytest.mark.parametrize("N,B,kernel,hetero", [(300, 130, "tc3", False), (300, 130, "tc", True), (1000, 256, "tc3", True),
+                                               (528, 128, "tc3", False)])
+def test_large_connectome_integrator_vs_oracle(N, B, kernel, hetero, oracle_lib):
+    """BASELINE configs[4] fast path (csrc/wc_big.cuh: one launch per Euler step, tcgen05 GEMM of the whole batch with the
+    node update fused onto the TMEM accumulator) against the float64 oracle on the same Philox streams: recorded E rows,
+    final (E, I, a_ie) and the coupling SC.E of the first step.  N = 300 / 528 exercise partial node slices and K padding."""
+    from nremmodfc_b200 import ops
+    from oracle import wc_oracle
+    SC = _random_sc(N, N)
+    rng = np.random.default_rng(N + 1)
+    n1, n2, n3 = 20, 30, 60
+    p = ops.make_params(N, n1, n2, n3, P=0.4, rhoE=0.18, seed=99)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    mG = rng.uniform(0.5, 1.5, N) if hetero else None
+    mS = rng.uniform(0.8, 1.2, N) if hetero else None
+    streams = rng.integers(0, 2 ** 62, B).astype(np.uint64)
+    E, fin, coup = ops.big_integrate_f32(p, SC, np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, streams, kernel=kernel,
+                                         want_coupling=True)
+    assert E.shape == (3, N, B) and fin.shape == (3, N, B) and coup.shape == (N, B)
+    tol = 5e-3 if kernel == "tc" else 2e-4
+    c0 = po["E0"] * SC.sum(axis=1) if isinstance(po, dict) else None
+    if c0 is not None:
+        # the tensor core truncates when it adds each K = 8 partial product to the FP32 accumulator: ~0.5 ulp bias per MMA,
+        # (N/8) x passes MMAs per output -> ~4e-6 at N = 300, ~1.3e-5 at N = 1000 (3xTF32 itself is ~1e-6)
+        assert np.max(np.abs(coup - c0[:, None]) / c0[:, None]) < (2e-3 if kernel == "tc" else 3e-5)
+    for b in (0, 31, 127, B - 1):
+        G = 0.16 + dG[b] * (mG if hetero else 1.0)
+        sg = 7.68 + ds[b] * (mS if hetero else 1.0)
+        Yo = oracle_lib.wc_run(SC, np.broadcast_to(G, N).copy(), np.broadcast_to(sg, N).copy(), n1, n2, n3, seed=99,
+                               stream=int(streams[b]), p=po)
+        fo = oracle_lib.wc_run(SC, np.broadcast_to(G, N).copy(), np.broadcast_to(sg, N).copy(), n1, n2, n3, seed=99,
+                               stream=int(streams[b]), p=po, want="final")
+        assert np.max(np.abs(E[:, :, b] - Yo[:, 0, :]) / np.abs(Yo[:, 0, :])) < tol
+        assert np.max(np.abs(fin[:, :, b] - fo) / np.abs(fo)) < tol
+
+
+def test_large_connectome_matches_small_path_statistics(aal90):
+    """The per-step kernel and the register-resident kernel integrate the same model with the same noise: on AAL90 (N = 90,
+    which both accept) their float32 trajectories agree to rounding over a short horizon, incl. an a_ie recombination."""
+    from nremmodfc_b200 import ops
+    p = ops.make_params(90, 100, 4200, 400, P=0.4, rhoE=0.18, seed=5)
+    B = 128
+    dG = np.linspace(-0.1, 0.02, B)
+    st = np.arange(B, dtype=np.uint64) + 11
+    E1, f1 = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=st, kernel="tc3")
+    E2, f2 = ops.big_integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=st, kernel="tc3")
+    assert np.max(np.abs(E1[0] - E2[0]) / np.abs(E1[0])) < 5e-3          # 0.43 s of chaotic float32 dynamics
+    assert np.max(np.abs(f1[2] - f2[2]) / np.abs(f1[2])) < 5e-3
