@@ -25,14 +25,14 @@ namespace nrem {
 constexpr int kBigNT = 256;                 // output nodes per CTA (= MMA N)
 constexpr int kBigKS = 4;                   // four-node groups per pipeline stage (16 input nodes, two K = 8 MMAs)
 constexpr int kBigStages = 4;
-constexpr int kBigEpiWarps = 8;
+constexpr int kBigEpiWarps = 16;
 constexpr int kBigThreads = (2 + kBigEpiWarps) * 32;
 constexpr int kBigCols = kBigNT / (kBigEpiWarps / 4);     // accumulator columns per epilogue warp
 constexpr uint32_t kBigAStage = kBigKS * kTile * 16;     // 8 KB per (hi | lo)
 constexpr uint32_t kBigBStage = kBigKS * kBigNT * 16;    // 16 KB per (hi | lo)
 constexpr uint32_t kBigLBO_A = kTile * 16;
 constexpr uint32_t kBigLBO_B = kBigNT * 16;
-constexpr uint32_t kBigTmemCols = 256;
+constexpr uint32_t kBigTmemCols = 512;              // 0..255 coupling accumulator, 256..511 the coupling-free part of the sigmoid argument
 constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
 template <int NPASS>
@@ -73,8 +73,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct BigGroup {            // state of one thread's 8 nodes (two four-node groups)
-    float4 eh[2], el[2], i[2], b[2], d[2];
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// wait for two 8-column loads; the registers are in/out operands so that no use can be hoisted above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[8], uint32_t (&q)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
+                 :: "memory");
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+struct BigQuad {             // state of one thread's four-node group
+    float4 eh, el, i, b, d;
 };
 
 template <int NPASS>
@@ -170,68 +187,98 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
         int ng = (N - node_base + 7) / 8;
         ng = ng < 0 ? 0 : (ng > kBigCols / 8 ? kBigCols / 8 : ng);
 
-        auto load8 = [&](int g, BigGroup& s) {
-            const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                s.eh[h] = A.Acur[idx + h * kTile];
-                s.el[h] = A.Acur[plane + idx + h * kTile];
-                s.i[h] = A.I4[idx + h * kTile];
-                s.b[h] = A.ab4[idx + h * kTile];
-                s.d[h] = A.ad4[idx + h * kTile];
-            }
+        auto load4 = [&](int qd, BigQuad& s) {
+            const size_t idx = rowbase + (size_t)((node_base >> 2) + qd) * kTile;
+            s.eh = A.Acur[idx];
+            s.el = A.Acur[plane + idx];
+            s.i = A.I4[idx];
+            s.b = A.ab4[idx];
+            s.d = A.ad4[idx];
         };
-        BigGroup cur, nxt;
-        if (ng > 0) load8(0, cur);
-        mbar_wait(accum, 0);
-        tc_fence_after();
-        for (int g = 0; g < ng; ++g) {
-            if (g + 1 < ng) load8(g + 1, nxt);
-            uint32_t cr[8];
-            tmem_ld8(tmem_mine + 8 * g, cr);
-            tmem_ld_wait8(cr);
-            const int node0 = node_base + 8 * g;
-            const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+        // -- phase 1, while the tensor core works: everything that does not need the coupling (noise, I and a_ie updates,
+        //    recording) and xp = a_ee E - a_ie I + P - mu + noise, parked in the spare TMEM columns 256..511
+        {
+            BigQuad cur, nxt;
+            const int nq = 2 * ng;
+            if (nq > 0) load4(0, cur);
+            for (int qd = 0; qd < nq; ++qd) {
+                if (qd + 1 < nq) load4(qd + 1, nxt);
+                const int node0 = node_base + 4 * qd;
+                const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
+                uint32_t xp4[4];
                 float z[4];
-                normals4f(philox4x32_10(A.step, (uint32_t)((node0 >> 2) + h), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
-                float E[4] = {cur.eh[h].x + cur.el[h].x, cur.eh[h].y + cur.el[h].y, cur.eh[h].z + cur.el[h].z, cur.eh[h].w + cur.el[h].w};
-                float I[4] = {cur.i[h].x, cur.i[h].y, cur.i[h].z, cur.i[h].w};
-                float ab[4] = {cur.b[h].x, cur.b[h].y, cur.b[h].z, cur.b[h].w};
-                float ad[4] = {cur.d[h].x, cur.d[h].y, cur.d[h].z, cur.d[h].w};
-                float hi[4], lo[4];
+                normals4f(philox4x32_10(A.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+                const float E[4] = {cur.eh.x + cur.el.x, cur.eh.y + cur.el.y, cur.eh.z + cur.el.z, cur.eh.w + cur.el.w};
+                float I[4] = {cur.i.x, cur.i.y, cur.i.z, cur.i.w};
+                float ab[4] = {cur.b.x, cur.b.y, cur.b.z, cur.b.w};
+                float ad[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int node = node0 + 4 * h + j;
+                    const int node = node0 + j;
                     const bool live = node < N;
-                    const float coup = __uint_as_float(cr[4 * h + j]);
                     if (A.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
                     if (live && A.rec) A.Ebuf[((size_t)A.row * N + node) * A.Bs + sim] = E[j];      // state BEFORE the update (WC:129-130)
-                    if (live && A.coup) A.coup[(size_t)node * A.Bs + sim] = coup;
                     float xp = fmaf(c.sq, z[j], Pmu);
                     xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(c.a_ee, E[j], xp)));
+                    xp4[j] = __float_as_uint(xp);
                     const float y = fmaf(-c.a_ii, I[j], fmaf(c.a_ei, E[j], nmu));
                     const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
                     const float dn = fmaf(I[j], fmaf(E[j], A.kA, nkr), ad[j]);
                     const float In = fmaf(c.kI, fmaf(fmaf(-c.rI, I[j], 1.0f), SI, -I[j]), I[j]);
-                    const float Gi = A.homo ? Gh : fmaf(dG, __ldg(A.mapG + node), G0);
-                    const float sg2 = A.homo ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
-                    const float x = fmaf(Gi, coup, xp);
-                    const float SE = rcpf(1.0f + ex2f(x * sg2));
-                    const float En = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
-                    hi[j] = live ? tf32_rn(En) : 0.f;
-                    lo[j] = live ? En - hi[j] : 0.f;
                     I[j] = live ? In : 0.f;
                     ad[j] = live ? dn : 0.f;
                 }
-                A.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                A.Anext[plane + idx + h * kTile] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                A.I4[idx + h * kTile] = make_float4(I[0], I[1], I[2], I[3]);
-                A.ad4[idx + h * kTile] = make_float4(ad[0], ad[1], ad[2], ad[3]);
-                if (A.recombine) A.ab4[idx + h * kTile] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+                A.I4[idx] = make_float4(I[0], I[1], I[2], I[3]);
+                A.ad4[idx] = make_float4(ad[0], ad[1], ad[2], ad[3]);
+                if (A.recombine) A.ab4[idx] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+                tmem_st4(tmem_mine + kBigNT + 4 * qd, xp4);
+                cur = nxt;
             }
-            cur = nxt;
+            tmem_st_wait();
+        }
+        // -- phase 2, after the last MMA: x = xp + G coup -> E(t+1), split and stored as the next A image
+        {
+            float4 ce[4], ne[4];                 // eh[0], eh[1], el[0], el[1]
+            auto loadE = [&](int g, float4 (&e)[4]) {
+                const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
+                e[0] = A.Acur[idx]; e[1] = A.Acur[idx + kTile];
+                e[2] = A.Acur[plane + idx]; e[3] = A.Acur[plane + idx + kTile];
+            };
+            if (ng > 0) loadE(0, ce);
+            mbar_wait(accum, 0);
+            tc_fence_after();
+            for (int g = 0; g < ng; ++g) {
+                if (g + 1 < ng) loadE(g + 1, ne);
+                uint32_t cr[8], xp8[8];
+                tmem_ld8(tmem_mine + 8 * g, cr);
+                tmem_ld8(tmem_mine + kBigNT + 8 * g, xp8);
+                tmem_ld_wait16(cr, xp8);
+                const int node0 = node_base + 8 * g;
+                const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float E[4] = {ce[h].x + ce[2 + h].x, ce[h].y + ce[2 + h].y, ce[h].z + ce[2 + h].z, ce[h].w + ce[2 + h].w};
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int node = node0 + 4 * h + j;
+                        const bool live = node < N;
+                        const float coup = __uint_as_float(cr[4 * h + j]);
+                        if (live && A.coup) A.coup[(size_t)node * A.Bs + sim] = coup;
+                        const float Gi = A.homo ? Gh : fmaf(dG, __ldg(A.mapG + node), G0);
+                        const float sg2 = A.homo ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
+                        const float x = fmaf(Gi, coup, __uint_as_float(xp8[4 * h + j]));
+                        const float SE = rcpf(1.0f + ex2f(x * sg2));
+                        const float En = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
+                        hi[j] = live ? tf32_rn(En) : 0.f;
+                        lo[j] = live ? En - hi[j] : 0.f;
+                    }
+                    A.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    A.Anext[plane + idx + h * kTile] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ce[k] = ne[k];
+            }
         }
     }
     tc_fence_before();
