@@ -729,8 +729,9 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     NREM_REQUIRE(p->nnodes >= 16 && p->nnodes <= 8192, "the large-connectome path supports 16 <= nnodes <= 8192");
     NREM_REQUIRE(!E_samples || nrec >= (p->n3 + p->downsamp - 1) / p->downsamp, "nrec too small");
     NREM_REQUIRE(final_state, "final_state is required");
-    const int k = resolve_kernel(kernel);
-    NREM_REQUIRE(k == 2 || k == 3, "kernel must be auto, tc or tc3");
+    const int k = kernel == 0 ? 4 : kernel;      // auto = TF32 + two BF16 correction passes
+    NREM_REQUIRE(k == 2 || k == 3 || k == 4, "kernel must be auto, tc, tc3 or tcb");
+    const int mixed = k == 4 ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int N = p->nnodes;
     const int Kpad = (int)round_up(N, 4 * kBigKS), KG = Kpad / 4, slices = (N + kBigNT - 1) / kBigNT;
@@ -752,7 +753,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     auto body = [&]() -> int {
         NREM_CUDA(cudaMemsetAsync(dev, 0, (size_t)o_b, st));            // images and state: padding nodes stay zero for ever
         const size_t nb = (size_t)slices * KG * kBigNT * 4;
-        big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, (float*)(base + o_b));
+        big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, mixed, (float*)(base + o_b));
         NREM_LAUNCHED();
         big_stage_maps_kernel<<<(Kpad + 255) / 256, 256, 0, st>>>(mapG, mapS, N, Kpad, (float*)(base + o_mg), (float*)(base + o_ms));
         NREM_LAUNCHED();
@@ -761,7 +762,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         NREM_LAUNCHED();
         BigArgs A;
         A.c = make_const(*p);
-        big_init_kernel<<<(unsigned)((nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)nf4, KG, (float4*)(base + o_a0), nf4, (float4*)(base + o_i),
+        big_init_kernel<<<(unsigned)((nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)nf4, KG, mixed, (float4*)(base + o_a0), nf4, (float4*)(base + o_i),
                                                                       (float4*)(base + o_ab));
         NREM_LAUNCHED();
         float4* img[2] = {(float4*)(base + o_a0), (float4*)(base + o_a1)};
@@ -771,10 +772,12 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
         A.Bs = Bs; A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
         A.Ebuf = E_samples;
-        if (k == 3) NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<3>()));
+        if (k == 4) NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<4>()));
+        else if (k == 3) NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<3>()));
         else NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<1>()));
         const dim3 grid((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
+        static const bool pdl = []() { const char* e = getenv("NREM_BIG_PDL"); return e ? atoi(e) != 0 : true; }();
         NREM_CUDA(cudaEventRecord(t0, st));
         for (int64_t s = 0; s < total; ++s) {
             const int ph = s < p->n1 ? 0 : (s < p->n1 + p->n2 ? 1 : 2);
@@ -786,13 +789,21 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             A.rec = (E_samples && ph == 2 && it % p->downsamp == 0) ? 1 : 0;
             A.row = A.rec ? it / p->downsamp : 0;
             A.coup = s == 0 ? coup_first : nullptr;
-            if (k == 3) wc_big_step_kernel<3><<<grid, kBigThreads, big_smem_bytes<3>(), st>>>(A);
-            else wc_big_step_kernel<1><<<grid, kBigThreads, big_smem_bytes<1>(), st>>>(A);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
+            cfg.dynamicSmemBytes = (size_t)(k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>());
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+            if (k == 4) NREM_CUDA(cudaLaunchKernelEx(&cfg, wc_big_step_kernel<4>, A));
+            else if (k == 3) NREM_CUDA(cudaLaunchKernelEx(&cfg, wc_big_step_kernel<3>, A));
+            else NREM_CUDA(cudaLaunchKernelEx(&cfg, wc_big_step_kernel<1>, A));
             NREM_LAUNCHED();
         }
         NREM_CUDA(cudaEventRecord(t1, st));
         const int64_t n = (int64_t)N * Bs;
-        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, Bs, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
+        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, Bs, mixed, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
                                                                       (const float*)A.ab4, (const float*)A.ad4, final_state);
         NREM_LAUNCHED();
         return NREM_OK;

@@ -17,7 +17,19 @@
 //   B image  [2 (hi, lo)][slice][KG][256 nodes][4]  SC rows of the slice's output nodes, staged once
 //   I, a_base, a_delta                               [tile][KG][128][4], updated in place (one owner thread per element)
 // KG = ceil(N/16)*4 four-node groups; padding nodes are zero in every image and are never written.
+//
+// Three precisions of the contraction (template MODE):
+//   1 "tc"   one TF32 pass (operands truncated to TF32 by the tensor core)
+//   3 "tc3"  3xTF32: Eh.Sh + El.Sh + Eh.Sl with FP32 residuals (El = E - Eh), 6 TF32 MMAs per 16 input nodes
+//   4 "tcb"  TF32 main pass on the raw FP32 operands (the tensor core ignores the low 13 mantissa bits: Eh = trunc(E)) plus
+//            the two correction passes  lo(E).S  and  E.lo(S)  (lo(x) = x - trunc(x) ~ 2^-10 x) as kind::f16 BF16 MMAs at twice
+//            the TF32 rate: BF16's 2^-9 rounding on a 2^-10 term leaves ~2^-19 ~ 2e-6 of the coupling, below the ~1e-5
+//            accumulation bias of the tensor core itself at N = 1000.  2 TF32 + 2 BF16 MMAs per 16 input nodes (-33 % time).
+//            Images: A = [F: float4 planes][L: bf16 lo(E)][H: bf16 E] with bf16 planes as [tile][KG/2][128 sims][8] (16 B rows),
+//            B likewise [F][H: bf16 S][L: bf16 lo(S)].
 #pragma once
+#include <cuda_bf16.h>
+
 #include "wc_tc.cuh"
 
 namespace nrem {
@@ -35,10 +47,23 @@ constexpr uint32_t kBigLBO_B = kBigNT * 16;
 constexpr uint32_t kBigTmemCols = 512;              // 0..255 coupling accumulator, 256..511 the coupling-free part of the sigmoid argument
 constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
-template <int NPASS>
-constexpr uint32_t big_stage_bytes() { return (NPASS == 3 ? 2u : 1u) * (kBigAStage + kBigBStage); }
-template <int NPASS>
-constexpr int big_smem_bytes() { return (int)(kBigStages * big_stage_bytes<NPASS>()) + 128; }
+template <int MODE>
+constexpr uint32_t big_stage_bytes() { return (MODE == 1 ? 1u : 2u) * (kBigAStage + kBigBStage); }
+template <int MODE>
+constexpr int big_smem_bytes() { return (int)(kBigStages * big_stage_bytes<MODE>()) + 128; }
+// kind::f16 instruction descriptor: D = F32, A = B = BF16 (format 1), K-major, N = 256, M = 128
+constexpr uint32_t kBigIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ uint32_t bf16x2(float lo_elem, float hi_elem) {       // {lo_elem in bits 0..15, hi_elem in 16..31}, RN
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
 
 struct BigArgs {
     BatchConst c;
@@ -94,12 +119,15 @@ struct BigQuad {             // state of one thread's four-node group
     float4 eh, el, i, b, d;
 };
 
-template <int NPASS>
+template <int MODE>
 __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    constexpr bool SPLIT = NPASS == 3;
-    constexpr uint32_t STAGE = (NPASS == 3 ? 2u : 1u) * (kBigAStage + kBigBStage);
-    constexpr uint32_t OFF_B = (SPLIT ? 2u : 1u) * kBigAStage;
+    constexpr bool SPLIT = MODE == 3;
+    constexpr bool MIXED = MODE == 4;
+    constexpr uint32_t STAGE = (MODE == 1 ? 1u : 2u) * (kBigAStage + kBigBStage);
+    // stage layout   MODE 1: [A 8K][B 16K]      MODE 3: [Ah 8K][Al 8K][Bh 16K][Bl 16K]
+    //                MODE 4: [Af 8K][Al bf16 4K][Ah bf16 4K][Bf 16K][Bh bf16 8K][Bl bf16 8K]
+    constexpr uint32_t OFF_B = (MODE == 1 ? 1u : 2u) * kBigAStage;
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + kBigStages * STAGE);
     uint64_t* empty = full + kBigStages;
     uint64_t* accum = empty + kBigStages;
@@ -110,6 +138,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     const BatchConst& c = A.c;
     const int N = c.N;
 
+    // programmatic dependent launch: let the next step's grid start its prologue as soon as SMs free up ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         for (int s = 0; s < kBigStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(accum, 1);
@@ -120,25 +150,41 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
-    const size_t plane = (size_t)A.tiles * A.KG * kTile;                 // float4 per (hi | lo) plane of an A image
+    const size_t plane = (size_t)A.tiles * A.KG * kTile;                 // float4 per FP32 plane of an A image
+    const size_t planeB = (size_t)A.slices * A.KG * kBigNT;              // float4 per FP32 plane of the B image
+    // ... and wait here until the previous step's grid has completed and its E(t), I, a_ie are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
             // ---- producer: one contiguous bulk copy per operand and stage ----
-            const char* a_hi = reinterpret_cast<const char*>(A.Acur + (size_t)tile * A.KG * kTile);
-            const char* a_lo = reinterpret_cast<const char*>(A.Acur + plane + (size_t)tile * A.KG * kTile);
-            const char* b_hi = reinterpret_cast<const char*>(A.Bimg + (size_t)slice * A.KG * kBigNT);
-            const char* b_lo = reinterpret_cast<const char*>(A.Bimg + ((size_t)A.slices + slice) * A.KG * kBigNT);
+            const char* a0 = reinterpret_cast<const char*>(A.Acur + (size_t)tile * A.KG * kTile);
+            const char* a1 = reinterpret_cast<const char*>(A.Acur + plane + (size_t)tile * A.KG * kTile);              // MODE 3: lo plane
+            const char* b0 = reinterpret_cast<const char*>(A.Bimg + (size_t)slice * A.KG * kBigNT);
+            const char* b1 = reinterpret_cast<const char*>(A.Bimg + planeB + (size_t)slice * A.KG * kBigNT);
+            // MODE 4: bf16 planes, 16-byte rows of 8 nodes: [tile][KG/2][128] and [slice][KG/2][256] uint4
+            const char* aL = reinterpret_cast<const char*>(A.Acur + plane) + (size_t)tile * (A.KG / 2) * kTile * 16;
+            const char* aH = aL + plane * 8;
+            const char* bH = reinterpret_cast<const char*>(A.Bimg + planeB) + (size_t)slice * (A.KG / 2) * kBigNT * 16;
+            const char* bL = bH + planeB * 8;
             const uint32_t base = smem_u32(smraw);
             for (int kt = 0; kt < KT; ++kt) {
                 const int s = kt % kBigStages;
                 mbar_wait(empty + s, (uint32_t)(((kt / kBigStages) & 1) ^ 1));
                 mbar_expect_tx(full + s, STAGE);
                 const uint32_t dst = base + (uint32_t)s * STAGE;
-                bulk_g2s(dst, a_hi + (size_t)kt * kBigAStage, kBigAStage, full + s);
-                if (SPLIT) bulk_g2s(dst + kBigAStage, a_lo + (size_t)kt * kBigAStage, kBigAStage, full + s);
-                bulk_g2s(dst + OFF_B, b_hi + (size_t)kt * kBigBStage, kBigBStage, full + s);
-                if (SPLIT) bulk_g2s(dst + OFF_B + kBigBStage, b_lo + (size_t)kt * kBigBStage, kBigBStage, full + s);
+                bulk_g2s(dst, a0 + (size_t)kt * kBigAStage, kBigAStage, full + s);
+                bulk_g2s(dst + OFF_B, b0 + (size_t)kt * kBigBStage, kBigBStage, full + s);
+                if (SPLIT) {
+                    bulk_g2s(dst + kBigAStage, a1 + (size_t)kt * kBigAStage, kBigAStage, full + s);
+                    bulk_g2s(dst + OFF_B + kBigBStage, b1 + (size_t)kt * kBigBStage, kBigBStage, full + s);
+                }
+                if (MIXED) {
+                    bulk_g2s(dst + kBigAStage, aL + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
+                    bulk_g2s(dst + kBigAStage + kBigAStage / 2, aH + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
+                    bulk_g2s(dst + OFF_B + kBigBStage, bH + (size_t)kt * (kBigBStage / 2), kBigBStage / 2, full + s);
+                    bulk_g2s(dst + OFF_B + kBigBStage + kBigBStage / 2, bL + (size_t)kt * (kBigBStage / 2), kBigBStage / 2, full + s);
+                }
             }
         }
         __syncwarp();
@@ -157,11 +203,22 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
 #pragma unroll
                 for (int k8 = 0; k8 < kBigKS / 2; ++k8) {
 #pragma unroll
-                    for (int pass = 0; pass < NPASS; ++pass) {
+                    for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
                         const uint64_t a0 = (pass == 1) ? ad_lo : ad_hi;
                         const uint64_t b0 = (pass == 2) ? bd_lo : bd_hi;
                         umma_tf32(tmem_d, a0 + (uint64_t)(k8 * ((2 * kBigLBO_A) >> 4)), b0 + (uint64_t)(k8 * ((2 * kBigLBO_B) >> 4)), kBigIdesc, acc);
                         acc = 1;
+                    }
+                }
+                if (MIXED) {
+                    // one K = 16 BF16 MMA per correction: the bf16 stage arrays are [2 eight-node groups][rows][16 B], i.e. the same
+                    // core-matrix geometry (LBO = rows x 16 B, SBO = 128 B) as a K = 8 TF32 slice
+                    const uint64_t aL = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO), aH = umma_desc(sa + kBigAStage + kBigAStage / 2, kBigLBO_A, kSBO);
+                    const uint64_t bH = umma_desc(sa + OFF_B + kBigBStage, kBigLBO_B, kSBO), bL = umma_desc(sa + OFF_B + kBigBStage + kBigBStage / 2, kBigLBO_B, kSBO);
+#pragma unroll
+                    for (int k16 = 0; k16 < kBigKS / 4; ++k16) {
+                        umma_bf16(tmem_d, aL + (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), bH + (uint64_t)(k16 * ((2 * kBigLBO_B) >> 4)), kBigIdescBf16, 1);
+                        umma_bf16(tmem_d, aH + (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), bL + (uint64_t)(k16 * ((2 * kBigLBO_B) >> 4)), kBigIdescBf16, 1);
                     }
                 }
                 umma_commit(empty + s);        // the stage may be refilled once these MMAs have read it
@@ -190,7 +247,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
         auto load4 = [&](int qd, BigQuad& s) {
             const size_t idx = rowbase + (size_t)((node_base >> 2) + qd) * kTile;
             s.eh = A.Acur[idx];
-            s.el = A.Acur[plane + idx];
+            if (!MIXED) s.el = A.Acur[plane + idx];
             s.i = A.I4[idx];
             s.b = A.ab4[idx];
             s.d = A.ad4[idx];
@@ -208,7 +265,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 uint32_t xp4[4];
                 float z[4];
                 normals4f(philox4x32_10(A.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
-                const float E[4] = {cur.eh.x + cur.el.x, cur.eh.y + cur.el.y, cur.eh.z + cur.el.z, cur.eh.w + cur.el.w};
+                float E[4] = {cur.eh.x, cur.eh.y, cur.eh.z, cur.eh.w};
+                if (!MIXED) { E[0] += cur.el.x; E[1] += cur.el.y; E[2] += cur.el.z; E[3] += cur.el.w; }
                 float I[4] = {cur.i.x, cur.i.y, cur.i.z, cur.i.w};
                 float ab[4] = {cur.b.x, cur.b.y, cur.b.z, cur.b.w};
                 float ad[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
@@ -236,13 +294,14 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             }
             tmem_st_wait();
         }
-        // -- phase 2, after the last MMA: x = xp + G coup -> E(t+1), split and stored as the next A image
+        // -- phase 2, after the last MMA: x = xp + G coup -> E(t+1), stored as the next A image
         {
-            float4 ce[4], ne[4];                 // eh[0], eh[1], el[0], el[1]
-            auto loadE = [&](int g, float4 (&e)[4]) {
+            constexpr int NE = MIXED ? 2 : 4;
+            float4 ce[NE], ne[NE];               // MODE 1/3: eh[0], eh[1], el[0], el[1];  MODE 4: E[0], E[1]
+            auto loadE = [&](int g, float4 (&e)[NE]) {
                 const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
                 e[0] = A.Acur[idx]; e[1] = A.Acur[idx + kTile];
-                e[2] = A.Acur[plane + idx]; e[3] = A.Acur[plane + idx + kTile];
+                if (!MIXED) { e[NE - 2] = A.Acur[plane + idx]; e[NE - 1] = A.Acur[plane + idx + kTile]; }
             };
             if (ng > 0) loadE(0, ce);
             mbar_wait(accum, 0);
@@ -255,10 +314,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 tmem_ld_wait16(cr, xp8);
                 const int node0 = node_base + 8 * g;
                 const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
+                float En[8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const float E[4] = {ce[h].x + ce[2 + h].x, ce[h].y + ce[2 + h].y, ce[h].z + ce[2 + h].z, ce[h].w + ce[2 + h].w};
-                    float hi[4], lo[4];
+                    float E[4] = {ce[h].x, ce[h].y, ce[h].z, ce[h].w};
+                    if (!MIXED) { E[0] += ce[NE - 2 + h].x; E[1] += ce[NE - 2 + h].y; E[2] += ce[NE - 2 + h].z; E[3] += ce[NE - 2 + h].w; }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int node = node0 + 4 * h + j;
@@ -269,15 +329,33 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                         const float sg2 = A.homo ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
                         const float x = fmaf(Gi, coup, __uint_as_float(xp8[4 * h + j]));
                         const float SE = rcpf(1.0f + ex2f(x * sg2));
-                        const float En = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
-                        hi[j] = live ? tf32_rn(En) : 0.f;
-                        lo[j] = live ? En - hi[j] : 0.f;
+                        const float e1 = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
+                        En[4 * h + j] = live ? e1 : 0.f;
                     }
-                    A.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    A.Anext[plane + idx + h * kTile] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                if (MIXED) {
+                    A.Anext[idx] = make_float4(En[0], En[1], En[2], En[3]);
+                    A.Anext[idx + kTile] = make_float4(En[4], En[5], En[6], En[7]);
+                    float lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) lo[j] = En[j] - tf32_trunc(En[j]);
+                    uint4* L = reinterpret_cast<uint4*>(A.Anext + plane);
+                    uint4* H = L + plane / 2;
+                    const size_t i8 = ((size_t)tile * (A.KG / 2) + (size_t)(node0 >> 3)) * kTile + r;
+                    L[i8] = make_uint4(bf16x2(lo[0], lo[1]), bf16x2(lo[2], lo[3]), bf16x2(lo[4], lo[5]), bf16x2(lo[6], lo[7]));
+                    H[i8] = make_uint4(bf16x2(En[0], En[1]), bf16x2(En[2], En[3]), bf16x2(En[4], En[5]), bf16x2(En[6], En[7]));
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float hi[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) hi[j] = tf32_rn(En[4 * h + j]);
+                        A.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        A.Anext[plane + idx + h * kTile] = make_float4(En[4 * h] - hi[0], En[4 * h + 1] - hi[1], En[4 * h + 2] - hi[2], En[4 * h + 3] - hi[3]);
+                    }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ce[k] = ne[k];
+                for (int k = 0; k < NE; ++k) ce[k] = ne[k];
             }
         }
     }
@@ -288,7 +366,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
 
 // ---- staging ---------------------------------------------------------------------------------------------------------
 // SC (float64 [N][N], row = target node) -> B image hi/lo
-__global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, float* Bimg) {
+__global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, int mixed, float* Bimg) {
     const size_t total = (size_t)slices * KG * kBigNT * 4;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -298,9 +376,18 @@ __global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, 
     const int kg = (int)(rest % KG), slice = (int)(rest / KG);
     const int n = slice * kBigNT + nl, k = kg * 4 + kk;
     const float v = (n < N && k < N) ? (float)CM[(size_t)n * N + k] : 0.f;
-    const float h = tf32_rn(v);
-    Bimg[idx] = h;
-    Bimg[total + idx] = v - h;
+    if (!mixed) {
+        const float h = tf32_rn(v);
+        Bimg[idx] = h;
+        Bimg[total + idx] = v - h;
+    } else {
+        Bimg[idx] = v;
+        __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(Bimg + total);       // [slice][KG/2][256][8]
+        __nv_bfloat16* L = H + total;
+        const size_t o = (((size_t)slice * (KG / 2) + (kg >> 1)) * kBigNT + nl) * 8 + (size_t)((kg & 1) * 4 + kk);
+        H[o] = __float2bfloat16_rn(v);
+        L[o] = __float2bfloat16_rn(v - tf32_trunc(v));
+    }
 }
 
 __global__ void big_stage_maps_kernel(const double* mapG, const double* mapS, int N, int Kpad, float* mG, float* mS) {
@@ -311,34 +398,44 @@ __global__ void big_stage_maps_kernel(const double* mapG, const double* mapS, in
 }
 
 // initial condition (netwWilsonCowanPlastic.py:90-99) into the images; every array was zeroed before
-__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, float4* A0, size_t plane, float4* I4, float4* ab4) {
+__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, float4* A0, size_t plane, float4* I4, float4* ab4) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index [tile][kg][r]
     if (idx >= nf4) return;
     const int kg = (int)((idx / kTile) % KG);
+    const int64_t tile = idx / ((int64_t)KG * kTile);
+    const int r = (int)(idx % kTile);
     float e[4], l[4], i[4], a[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const bool live = kg * 4 + j < c.N;
-        e[j] = live ? tf32_rn(c.E0) : 0.f;
-        l[j] = live ? c.E0 - e[j] : 0.f;
+        e[j] = live ? (mixed ? c.E0 : tf32_rn(c.E0)) : 0.f;
+        l[j] = live ? (mixed ? c.E0 - tf32_trunc(c.E0) : c.E0 - e[j]) : 0.f;
         i[j] = live ? c.I0 : 0.f;
         a[j] = live ? c.a0 : 0.f;
     }
     A0[idx] = make_float4(e[0], e[1], e[2], e[3]);
-    A0[plane + idx] = make_float4(l[0], l[1], l[2], l[3]);
+    if (!mixed) {
+        A0[plane + idx] = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+        __nv_bfloat16* L = reinterpret_cast<__nv_bfloat16*>(A0 + plane);        // [tile][KG/2][128][8]
+        __nv_bfloat16* H = L + plane * 4;
+        const size_t o = (((size_t)tile * (KG / 2) + (kg >> 1)) * kTile + r) * 8 + (size_t)((kg & 1) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { L[o + j] = __float2bfloat16_rn(l[j]); H[o + j] = __float2bfloat16_rn(e[j]); }
+    }
     I4[idx] = make_float4(i[0], i[1], i[2], i[3]);
     ab4[idx] = make_float4(a[0], a[1], a[2], a[3]);
 }
 
 // images -> final state [3][N][Bs] (E, I, a_ie), simulation fastest
-__global__ void big_export_kernel(int N, int KG, int64_t Bs, const float* Aimg, size_t plane_f, const float* I, const float* ab,
+__global__ void big_export_kernel(int N, int KG, int64_t Bs, int mixed, const float* Aimg, size_t plane_f, const float* I, const float* ab,
                                   const float* ad, float* fin) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= (int64_t)N * Bs) return;
     const int64_t sim = k % Bs;
     const int node = (int)(k / Bs);
     const size_t src = (((size_t)(sim / kTile) * KG + (node >> 2)) * kTile + (size_t)(sim % kTile)) * 4 + (node & 3);
-    fin[k] = Aimg[src] + Aimg[plane_f + src];
+    fin[k] = mixed ? Aimg[src] : Aimg[src] + Aimg[plane_f + src];
     fin[(int64_t)N * Bs + k] = I[src];
     fin[2 * (int64_t)N * Bs + k] = ab[src] + ad[src];
 }

@@ -232,7 +232,7 @@ def kuramoto(bold, device=None):
     return (float(out[0, 0]), float(out[0, 1])) if sq else (out[:, 0], out[:, 1])
 
 
-KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3}
+KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3, "tcb": 4}
 
 
 def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=None, streams=None, kernel="fma",

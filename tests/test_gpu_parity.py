@@ -487,7 +487,8 @@ def _random_sc(N, seed):
 
 
 @pytest.mark.parametrize("N,B,kernel,hetero", [(300, 130, "tc3", False), (300, 130, "tc", True), (1000, 256, "tc3", True),
-                                               (528, 128, "tc3", False)])
+                                               (528, 128, "tc3", False), (300, 130, "tcb", False), (1000, 256, "tcb", True),
+                                               (528, 128, "auto", True)])
 def test_large_connectome_integrator_vs_oracle(N, B, kernel, hetero, oracle_lib):
     """BASELINE configs[4] fast path (csrc/wc_big.cuh: one launch per Euler step, tcgen05 GEMM of the whole batch with the
     node update fused onto the TMEM accumulator) against the float64 oracle on the same Philox streams: recorded E rows,
