@@ -772,9 +772,16 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
         A.Bs = Bs; A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
         A.Ebuf = E_samples;
-        if (k == 4) NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<4>()));
-        else if (k == 3) NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<3>()));
-        else NREM_CUDA(cudaFuncSetAttribute(wc_big_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_smem_bytes<1>()));
+        const bool fullN = N % 8 == 0, homoN = A.homo != 0;
+        auto pick = [&](auto mode) -> void (*)(const BigArgs) {
+            constexpr int M = decltype(mode)::value;
+            if (fullN) return homoN ? wc_big_step_kernel<M, true, true> : wc_big_step_kernel<M, true, false>;
+            return homoN ? wc_big_step_kernel<M, false, true> : wc_big_step_kernel<M, false, false>;
+        };
+        void (*kern)(const BigArgs) = k == 4 ? pick(std::integral_constant<int, 4>{})
+                                    : k == 3 ? pick(std::integral_constant<int, 3>{}) : pick(std::integral_constant<int, 1>{});
+        const int smem = k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>();
+        NREM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const dim3 grid((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
         static const bool pdl = []() { const char* e = getenv("NREM_BIG_PDL"); return e ? atoi(e) != 0 : true; }();
@@ -791,14 +798,12 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             A.coup = s == 0 ? coup_first : nullptr;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
-            cfg.dynamicSmemBytes = (size_t)(k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>());
+            cfg.dynamicSmemBytes = (size_t)smem;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-            if (k == 4) NREM_CUDA(cudaLaunchKernelEx(&cfg, wc_big_step_kernel<4>, A));
-            else if (k == 3) NREM_CUDA(cudaLaunchKernelEx(&cfg, wc_big_step_kernel<3>, A));
-            else NREM_CUDA(cudaLaunchKernelEx(&cfg, wc_big_step_kernel<1>, A));
+            NREM_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
             NREM_LAUNCHED();
         }
         NREM_CUDA(cudaEventRecord(t1, st));

@@ -119,7 +119,8 @@ struct BigQuad {             // state of one thread's four-node group
     float4 eh, el, i, b, d;
 };
 
-template <int MODE>
+// FULL: N is a multiple of 8, so no node of a processed 8-node group is padding.  HOMO: no per-node maps (G, sigma per simulation)
+template <int MODE, bool FULL, bool HOMO>
 __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr bool SPLIT = MODE == 3;
@@ -244,24 +245,27 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
         int ng = (N - node_base + 7) / 8;
         ng = ng < 0 ? 0 : (ng > kBigCols / 8 ? kBigCols / 8 : ng);
 
-        auto load4 = [&](int qd, BigQuad& s) {
-            const size_t idx = rowbase + (size_t)((node_base >> 2) + qd) * kTile;
-            s.eh = A.Acur[idx];
-            if (!MIXED) s.el = A.Acur[plane + idx];
-            s.i = A.I4[idx];
-            s.b = A.ab4[idx];
-            s.d = A.ad4[idx];
-        };
         // -- phase 1, while the tensor core works: everything that does not need the coupling (noise, I and a_ie updates,
-        //    recording) and xp = a_ee E - a_ie I + P - mu + noise, parked in the spare TMEM columns 256..511
+        //    recording) and xp = a_ee E - a_ie I + P - mu + noise, parked in the spare TMEM columns 256..511.
+        //    The state of quad qd + 1 is requested before quad qd is computed (two quads ahead measured 2 % slower in the
+        //    MMA-bound modes: register pressure).
         {
-            BigQuad cur, nxt;
             const int nq = 2 * ng;
+            const size_t idx0 = rowbase + (size_t)(node_base >> 2) * kTile;
+            auto load4 = [&](int qd, BigQuad& s) {
+                const size_t idx = idx0 + (size_t)qd * kTile;
+                s.eh = A.Acur[idx];
+                if (!MIXED) s.el = A.Acur[plane + idx];
+                s.i = A.I4[idx];
+                s.b = A.ab4[idx];
+                s.d = A.ad4[idx];
+            };
+            BigQuad cur, n1;
             if (nq > 0) load4(0, cur);
             for (int qd = 0; qd < nq; ++qd) {
-                if (qd + 1 < nq) load4(qd + 1, nxt);
+                if (qd + 1 < nq) load4(qd + 1, n1);
                 const int node0 = node_base + 4 * qd;
-                const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
+                const size_t idx = idx0 + (size_t)qd * kTile;
                 uint32_t xp4[4];
                 float z[4];
                 normals4f(philox4x32_10(A.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int node = node0 + j;
-                    const bool live = node < N;
+                    const bool live = FULL || node < N;
                     if (A.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
                     if (live && A.rec) A.Ebuf[((size_t)A.row * N + node) * A.Bs + sim] = E[j];      // state BEFORE the update (WC:129-130)
                     float xp = fmaf(c.sq, z[j], Pmu);
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 A.ad4[idx] = make_float4(ad[0], ad[1], ad[2], ad[3]);
                 if (A.recombine) A.ab4[idx] = make_float4(ab[0], ab[1], ab[2], ab[3]);
                 tmem_st4(tmem_mine + kBigNT + 4 * qd, xp4);
-                cur = nxt;
+                cur = n1;
             }
             tmem_st_wait();
         }
@@ -314,6 +318,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 tmem_ld_wait16(cr, xp8);
                 const int node0 = node_base + 8 * g;
                 const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
+                if (A.coup) {                    // test hook (first step only)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (node0 + j < N) A.coup[(size_t)(node0 + j) * A.Bs + sim] = __uint_as_float(cr[j]);
+                }
                 float En[8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -322,11 +331,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int node = node0 + 4 * h + j;
-                        const bool live = node < N;
+                        const bool live = FULL || node < N;
                         const float coup = __uint_as_float(cr[4 * h + j]);
-                        if (live && A.coup) A.coup[(size_t)node * A.Bs + sim] = coup;
-                        const float Gi = A.homo ? Gh : fmaf(dG, __ldg(A.mapG + node), G0);
-                        const float sg2 = A.homo ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
+                        const float Gi = HOMO ? Gh : fmaf(dG, __ldg(A.mapG + node), G0);
+                        const float sg2 = HOMO ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
                         const float x = fmaf(Gi, coup, __uint_as_float(xp8[4 * h + j]));
                         const float SE = rcpf(1.0f + ex2f(x * sg2));
                         const float e1 = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
