@@ -777,38 +777,72 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         A.Bs = Bs; A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
         A.Ebuf = E_samples;
         const bool fullN = N % 8 == 0, homoN = A.homo != 0;
-        auto pick = [&](auto mode) -> void (*)(const BigArgs) {
+        auto pick = [&](auto mode, auto persist) -> void (*)(const BigArgs) {
             constexpr int M = decltype(mode)::value;
-            if (fullN) return homoN ? wc_big_step_kernel<M, true, true> : wc_big_step_kernel<M, true, false>;
-            return homoN ? wc_big_step_kernel<M, false, true> : wc_big_step_kernel<M, false, false>;
+            constexpr bool P = decltype(persist)::value;
+            if (fullN) return homoN ? wc_big_step_kernel<M, true, true, P> : wc_big_step_kernel<M, true, false, P>;
+            return homoN ? wc_big_step_kernel<M, false, true, P> : wc_big_step_kernel<M, false, false, P>;
         };
-        void (*kern)(const BigArgs) = k == 4 ? pick(std::integral_constant<int, 4>{})
-                                    : k == 3 ? pick(std::integral_constant<int, 3>{}) : pick(std::integral_constant<int, 1>{});
+        auto pick2 = [&](auto persist) -> void (*)(const BigArgs) {
+            return k == 4 ? pick(std::integral_constant<int, 4>{}, persist)
+                 : k == 3 ? pick(std::integral_constant<int, 3>{}, persist) : pick(std::integral_constant<int, 1>{}, persist);
+        };
         const int smem = k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>();
-        NREM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const dim3 grid((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
         static const bool pdl = []() { const char* e = getenv("NREM_BIG_PDL"); return e ? atoi(e) != 0 : true; }();
+        const char* env_persist = getenv("NREM_BIG_PERSIST");          // read per call so that tests can exercise both modes
+        const bool want_persist = env_persist ? atoi(env_persist) != 0 : false;   // measured 3-10 % slower than per-step launches + PDL
+        A.img[0] = img[0]; A.img[1] = img[1];
+        A.n1 = (uint32_t)p->n1; A.n12 = (uint32_t)(p->n1 + p->n2); A.downsamp = p->downsamp;
+        for (int ph = 0; ph < 3; ++ph) A.kA3[ph] = (float)(p->dtSim / p->tau_ip[ph]);
+        A.nsteps = 1;
+        // Persistent mode (NREM_BIG_PERSIST=1): the node slices of a tile form one thread-block cluster that runs all steps (one
+        // barrier.cluster per step, no launches).  Needs the cluster to fit the portable size and to be schedulable with this much
+        // shared memory.  Correct (tests run both modes) but on B200 it measured 42.6-44.1 us/step against 41.3-42.2 for one launch
+        // per step with programmatic dependent launch (tc3: 52-54 vs 47.7), so it is not the default.
+        bool persist = want_persist && slices <= 8 && total > 0;
+        void (*kern_p)(const BigArgs) = pick2(std::true_type{});
+        cudaLaunchConfig_t cfgp = {};
+        cudaLaunchAttribute atp[1];
+        if (persist) {
+            NREM_CUDA(cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            cfgp.gridDim = grid; cfgp.blockDim = dim3(kBigThreads); cfgp.stream = st; cfgp.dynamicSmemBytes = (size_t)smem;
+            atp[0].id = cudaLaunchAttributeClusterDimension;
+            atp[0].val.clusterDim.x = (unsigned)slices; atp[0].val.clusterDim.y = 1; atp[0].val.clusterDim.z = 1;
+            cfgp.attrs = atp; cfgp.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern_p, &cfgp) != cudaSuccess || nclusters < 1) { cudaGetLastError(); persist = false; }
+        }
         NREM_CUDA(cudaEventRecord(t0, st));
-        for (int64_t s = 0; s < total; ++s) {
-            const int ph = s < p->n1 ? 0 : (s < p->n1 + p->n2 ? 1 : 2);
-            const int64_t it = s - p->n1 - p->n2;
-            A.Acur = img[s & 1]; A.Anext = img[(s + 1) & 1];
-            A.step = (uint32_t)s;
-            A.kA = (float)(p->dtSim / p->tau_ip[ph]);
-            A.recombine = (s != 0 && (s & (int64_t)(kRecombine - 1)) == 0) ? 1 : 0;
-            A.rec = (E_samples && ph == 2 && it % p->downsamp == 0) ? 1 : 0;
-            A.row = A.rec ? it / p->downsamp : 0;
-            A.coup = s == 0 ? coup_first : nullptr;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
-            cfg.dynamicSmemBytes = (size_t)smem;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-            NREM_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
+        if (persist) {
+            A.step = 0; A.nsteps = (int)std::min<int64_t>(total, 0x7fffffff);
+            A.Acur = nullptr; A.Anext = nullptr; A.kA = 0.f; A.recombine = 0; A.rec = 0; A.row = 0; A.coup = coup_first;
+            NREM_CUDA(cudaLaunchKernelEx(&cfgp, kern_p, A));
             NREM_LAUNCHED();
+        } else {
+            void (*kern)(const BigArgs) = pick2(std::false_type{});
+            NREM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            for (int64_t s = 0; s < total; ++s) {
+                const int ph = s < p->n1 ? 0 : (s < p->n1 + p->n2 ? 1 : 2);
+                const int64_t it = s - p->n1 - p->n2;
+                A.Acur = img[s & 1]; A.Anext = img[(s + 1) & 1];
+                A.step = (uint32_t)s;
+                A.kA = A.kA3[ph];
+                A.recombine = (s != 0 && (s & (int64_t)(kRecombine - 1)) == 0) ? 1 : 0;
+                A.rec = (E_samples && ph == 2 && it % p->downsamp == 0) ? 1 : 0;
+                A.row = A.rec ? it / p->downsamp : 0;
+                A.coup = s == 0 ? coup_first : nullptr;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
+                cfg.dynamicSmemBytes = (size_t)smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+                NREM_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
+                NREM_LAUNCHED();
+            }
         }
         NREM_CUDA(cudaEventRecord(t1, st));
         const int64_t n = (int64_t)N * Bs;

@@ -87,7 +87,46 @@ struct BigArgs {
     int64_t row;
     float* Ebuf;               // [rows][N][Bs]
     float* coup;               // optional [N][Bs]: the coupling SC.E(t) of this step (tests)
+    // persistent (cluster) mode: the launch runs `nsteps` Euler steps starting at global step `step`; the per-step quantities above
+    // (kA, recombine, rec, row, coup, and which image is E(t)) are then derived in the kernel from the step index
+    int nsteps;
+    uint32_t n1, n12;          // phase boundaries: steps [0, n1) phase 1, [n1, n12) phase 2, the rest phase 3 (recording)
+    float kA3[3];              // dtSim / tau_ip per phase
+    int downsamp;
+    float4* img[2];            // the two A images; E(t) of global step s is img[s & 1]
 };
+
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+struct BigStep {               // per-step quantities of the persistent mode
+    const float4* Acur;
+    float4* Anext;
+    uint32_t step;
+    float kA;
+    int recombine, rec;
+    int64_t row;
+    float* coup;
+};
+__device__ __forceinline__ BigStep big_step_of(const BigArgs& A, int it, bool persist) {
+    BigStep S;
+    if (!persist) {
+        S.Acur = A.Acur; S.Anext = A.Anext; S.step = A.step; S.kA = A.kA; S.recombine = A.recombine; S.rec = A.rec; S.row = A.row; S.coup = A.coup;
+        return S;
+    }
+    const uint32_t s = A.step + (uint32_t)it;
+    S.step = s;
+    S.Acur = A.img[s & 1]; S.Anext = A.img[(s + 1) & 1];
+    const int ph = s < A.n1 ? 0 : (s < A.n12 ? 1 : 2);
+    S.kA = A.kA3[ph];
+    S.recombine = (s != 0 && (s & (kRecombine - 1)) == 0) ? 1 : 0;
+    const uint32_t r = s - A.n12;
+    S.rec = (A.Ebuf && ph == 2 && r % (uint32_t)A.downsamp == 0) ? 1 : 0;
+    S.row = S.rec ? (int64_t)(r / (uint32_t)A.downsamp) : 0;
+    S.coup = s == 0 ? A.coup : nullptr;
+    return S;
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -120,7 +159,9 @@ struct BigQuad {             // state of one thread's four-node group
 };
 
 // FULL: N is a multiple of 8, so no node of a processed 8-node group is padding.  HOMO: no per-node maps (G, sigma per simulation)
-template <int MODE, bool FULL, bool HOMO>
+// PERSIST: launched as thread-block clusters of `slices` CTAs (the node slices of one 128-simulation tile, which depend only on each
+//          other); the cluster runs A.nsteps Euler steps with one barrier.cluster per step instead of one launch per step.
+template <int MODE, bool FULL, bool HOMO, bool PERSIST>
 __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr bool SPLIT = MODE == 3;
@@ -139,8 +180,9 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     const BatchConst& c = A.c;
     const int N = c.N;
 
+    const int nsteps = PERSIST ? A.nsteps : 1;
     // programmatic dependent launch: let the next step's grid start its prologue as soon as SMs free up ...
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!PERSIST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         for (int s = 0; s < kBigStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(accum, 1);
@@ -154,24 +196,27 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     const size_t plane = (size_t)A.tiles * A.KG * kTile;                 // float4 per FP32 plane of an A image
     const size_t planeB = (size_t)A.slices * A.KG * kBigNT;              // float4 per FP32 plane of the B image
     // ... and wait here until the previous step's grid has completed and its E(t), I, a_ie are visible
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!PERSIST) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
+      uint32_t ring = 0;                                  // stages issued so far (continues across the steps of a persistent launch)
+      for (int it = 0; it < nsteps; ++it) {
         if (lane == 0) {
             // ---- producer: one contiguous bulk copy per operand and stage ----
-            const char* a0 = reinterpret_cast<const char*>(A.Acur + (size_t)tile * A.KG * kTile);
-            const char* a1 = reinterpret_cast<const char*>(A.Acur + plane + (size_t)tile * A.KG * kTile);              // MODE 3: lo plane
+            const float4* Acur = big_step_of(A, it, PERSIST).Acur;
+            const char* a0 = reinterpret_cast<const char*>(Acur + (size_t)tile * A.KG * kTile);
+            const char* a1 = reinterpret_cast<const char*>(Acur + plane + (size_t)tile * A.KG * kTile);              // MODE 3: lo plane
             const char* b0 = reinterpret_cast<const char*>(A.Bimg + (size_t)slice * A.KG * kBigNT);
             const char* b1 = reinterpret_cast<const char*>(A.Bimg + planeB + (size_t)slice * A.KG * kBigNT);
             // MODE 4: bf16 planes, 16-byte rows of 8 nodes: [tile][KG/2][128] and [slice][KG/2][256] uint4
-            const char* aL = reinterpret_cast<const char*>(A.Acur + plane) + (size_t)tile * (A.KG / 2) * kTile * 16;
+            const char* aL = reinterpret_cast<const char*>(Acur + plane) + (size_t)tile * (A.KG / 2) * kTile * 16;
             const char* aH = aL + plane * 8;
             const char* bH = reinterpret_cast<const char*>(A.Bimg + planeB) + (size_t)slice * (A.KG / 2) * kBigNT * 16;
             const char* bL = bH + planeB * 8;
             const uint32_t base = smem_u32(smraw);
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % kBigStages;
-                mbar_wait(empty + s, (uint32_t)(((kt / kBigStages) & 1) ^ 1));
+            for (int kt = 0; kt < KT; ++kt, ++ring) {
+                const int s = (int)(ring % kBigStages);
+                mbar_wait(empty + s, (uint32_t)(((ring / kBigStages) & 1) ^ 1));
                 mbar_expect_tx(full + s, STAGE);
                 const uint32_t dst = base + (uint32_t)s * STAGE;
                 bulk_g2s(dst, a0 + (size_t)kt * kBigAStage, kBigAStage, full + s);
@@ -189,14 +234,19 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             }
         }
         __syncwarp();
+        if (PERSIST) { cluster_arrive_release(); cluster_wait_acquire(); }      // E(t+1) of all node slices is written and visible
+      }
     } else if (warp == 1) {
+      uint32_t ring = 0;
+      for (int it = 0; it < nsteps; ++it) {
         if (lane == 0) {
             // ---- MMA issuer ----
             const uint32_t base = smem_u32(smraw);
             uint32_t acc = 0;
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % kBigStages;
-                mbar_wait(full + s, (uint32_t)((kt / kBigStages) & 1));
+            tc_fence_after();                              // (persistent: the epilogue's TMEM reads of the previous step are done)
+            for (int kt = 0; kt < KT; ++kt, ++ring) {
+                const int s = (int)(ring % kBigStages);
+                mbar_wait(full + s, (uint32_t)((ring / kBigStages) & 1));
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)s * STAGE;
                 const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO);
@@ -227,6 +277,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             umma_commit(accum);
         }
         __syncwarp();
+        if (PERSIST) { cluster_arrive_release(); cluster_wait_acquire(); }
+      }
     } else {
         // ---- epilogue: the node update of (128 sims) x (256 nodes), fused onto the TMEM accumulator ----
         const int q = warp & 3;                               // TMEM lane quarter this warp may read
@@ -240,11 +292,14 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
         const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
         const uint64_t strm = A.streams[sim];
         const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
-        const float Pmu = c.P - c.mu, nmu = -c.mu, nkr = -A.kA * c.rhoE;
+        const float Pmu = c.P - c.mu, nmu = -c.mu;
         const float Gh = G0 + dG, sgh = sg0 + dsg;
         int ng = (N - node_base + 7) / 8;
         ng = ng < 0 ? 0 : (ng > kBigCols / 8 ? kBigCols / 8 : ng);
 
+      for (int it = 0; it < nsteps; ++it) {
+        const BigStep S = big_step_of(A, it, PERSIST);
+        const float nkr = -S.kA * c.rhoE;
         // -- phase 1, while the tensor core works: everything that does not need the coupling (noise, I and a_ie updates,
         //    recording) and xp = a_ee E - a_ie I + P - mu + noise, parked in the spare TMEM columns 256..511.
         //    The state of quad qd + 1 is requested before quad qd is computed (two quads ahead measured 2 % slower in the
@@ -254,8 +309,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             const size_t idx0 = rowbase + (size_t)(node_base >> 2) * kTile;
             auto load4 = [&](int qd, BigQuad& s) {
                 const size_t idx = idx0 + (size_t)qd * kTile;
-                s.eh = A.Acur[idx];
-                if (!MIXED) s.el = A.Acur[plane + idx];
+                s.eh = S.Acur[idx];
+                if (!MIXED) s.el = S.Acur[plane + idx];
                 s.i = A.I4[idx];
                 s.b = A.ab4[idx];
                 s.d = A.ad4[idx];
@@ -268,7 +323,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 const size_t idx = idx0 + (size_t)qd * kTile;
                 uint32_t xp4[4];
                 float z[4];
-                normals4f(philox4x32_10(A.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+                normals4f(philox4x32_10(S.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
                 float E[4] = {cur.eh.x, cur.eh.y, cur.eh.z, cur.eh.w};
                 if (!MIXED) { E[0] += cur.el.x; E[1] += cur.el.y; E[2] += cur.el.z; E[3] += cur.el.w; }
                 float I[4] = {cur.i.x, cur.i.y, cur.i.z, cur.i.w};
@@ -278,21 +333,21 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 for (int j = 0; j < 4; ++j) {
                     const int node = node0 + j;
                     const bool live = FULL || node < N;
-                    if (A.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
-                    if (live && A.rec) A.Ebuf[((size_t)A.row * N + node) * A.Bs + sim] = E[j];      // state BEFORE the update (WC:129-130)
+                    if (S.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
+                    if (live && S.rec) A.Ebuf[((size_t)S.row * N + node) * A.Bs + sim] = E[j];      // state BEFORE the update (WC:129-130)
                     float xp = fmaf(c.sq, z[j], Pmu);
                     xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(c.a_ee, E[j], xp)));
                     xp4[j] = __float_as_uint(xp);
                     const float y = fmaf(-c.a_ii, I[j], fmaf(c.a_ei, E[j], nmu));
                     const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
-                    const float dn = fmaf(I[j], fmaf(E[j], A.kA, nkr), ad[j]);
+                    const float dn = fmaf(I[j], fmaf(E[j], S.kA, nkr), ad[j]);
                     const float In = fmaf(c.kI, fmaf(fmaf(-c.rI, I[j], 1.0f), SI, -I[j]), I[j]);
                     I[j] = live ? In : 0.f;
                     ad[j] = live ? dn : 0.f;
                 }
                 A.I4[idx] = make_float4(I[0], I[1], I[2], I[3]);
                 A.ad4[idx] = make_float4(ad[0], ad[1], ad[2], ad[3]);
-                if (A.recombine) A.ab4[idx] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+                if (S.recombine) A.ab4[idx] = make_float4(ab[0], ab[1], ab[2], ab[3]);
                 tmem_st4(tmem_mine + kBigNT + 4 * qd, xp4);
                 cur = n1;
             }
@@ -304,11 +359,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             float4 ce[NE], ne[NE];               // MODE 1/3: eh[0], eh[1], el[0], el[1];  MODE 4: E[0], E[1]
             auto loadE = [&](int g, float4 (&e)[NE]) {
                 const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
-                e[0] = A.Acur[idx]; e[1] = A.Acur[idx + kTile];
-                if (!MIXED) { e[NE - 2] = A.Acur[plane + idx]; e[NE - 1] = A.Acur[plane + idx + kTile]; }
+                e[0] = S.Acur[idx]; e[1] = S.Acur[idx + kTile];
+                if (!MIXED) { e[NE - 2] = S.Acur[plane + idx]; e[NE - 1] = S.Acur[plane + idx + kTile]; }
             };
             if (ng > 0) loadE(0, ce);
-            mbar_wait(accum, 0);
+            mbar_wait(accum, (uint32_t)(it & 1));
             tc_fence_after();
             for (int g = 0; g < ng; ++g) {
                 if (g + 1 < ng) loadE(g + 1, ne);
@@ -318,10 +373,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 tmem_ld_wait16(cr, xp8);
                 const int node0 = node_base + 8 * g;
                 const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
-                if (A.coup) {                    // test hook (first step only)
+                if (S.coup) {                    // test hook (first step only)
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (node0 + j < N) A.coup[(size_t)(node0 + j) * A.Bs + sim] = __uint_as_float(cr[j]);
+                        if (node0 + j < N) S.coup[(size_t)(node0 + j) * A.Bs + sim] = __uint_as_float(cr[j]);
                 }
                 float En[8];
 #pragma unroll
@@ -342,12 +397,12 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                     }
                 }
                 if (MIXED) {
-                    A.Anext[idx] = make_float4(En[0], En[1], En[2], En[3]);
-                    A.Anext[idx + kTile] = make_float4(En[4], En[5], En[6], En[7]);
+                    S.Anext[idx] = make_float4(En[0], En[1], En[2], En[3]);
+                    S.Anext[idx + kTile] = make_float4(En[4], En[5], En[6], En[7]);
                     float lo[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) lo[j] = En[j] - tf32_trunc(En[j]);
-                    uint4* L = reinterpret_cast<uint4*>(A.Anext + plane);
+                    uint4* L = reinterpret_cast<uint4*>(S.Anext + plane);
                     uint4* H = L + plane / 2;
                     const size_t i8 = ((size_t)tile * (A.KG / 2) + (size_t)(node0 >> 3)) * kTile + r;
                     L[i8] = make_uint4(bf16x2(lo[0], lo[1]), bf16x2(lo[2], lo[3]), bf16x2(lo[4], lo[5]), bf16x2(lo[6], lo[7]));
@@ -358,14 +413,24 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                         float hi[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) hi[j] = tf32_rn(En[4 * h + j]);
-                        A.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        A.Anext[plane + idx + h * kTile] = make_float4(En[4 * h] - hi[0], En[4 * h + 1] - hi[1], En[4 * h + 2] - hi[2], En[4 * h + 3] - hi[3]);
+                        S.Anext[idx + h * kTile] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        S.Anext[plane + idx + h * kTile] = make_float4(En[4 * h] - hi[0], En[4 * h + 1] - hi[1], En[4 * h + 2] - hi[2], En[4 * h + 3] - hi[3]);
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < NE; ++k) ce[k] = ne[k];
             }
         }
+            if (PERSIST) {
+            // E(t+1), I, a_ie of this CTA's node slice are written: make them visible to the other slices' bulk copies (async proxy) ...
+            if (A.nsteps < 0) __threadfence();       // (never: barrier.cluster release/acquire already orders the stores at cluster scope)
+            fence_proxy_async_all();
+            tc_fence_before();                 // ... and order this step's TMEM reads before the next step's MMAs
+            cluster_arrive_release();
+            cluster_wait_acquire();
+            tc_fence_after();
+        }
+      }
     }
     tc_fence_before();
     __syncthreads();

@@ -524,6 +524,24 @@ def test_large_connectome_integrator_vs_oracle(N, B, kernel, hetero, oracle_lib)
         assert np.max(np.abs(fin[:, :, b] - fo) / np.abs(fo)) < tol
 
 
+def test_large_connectome_persistent_cluster_mode_is_bit_identical(monkeypatch):
+    """NREM_BIG_PERSIST=1 runs the same step code inside one thread-block cluster per tile (barrier.cluster per step instead of a
+    launch per step): the arithmetic is identical, so E samples and final state must match the per-step launches bit for bit."""
+    from nremmodfc_b200 import ops
+    N, B = 520, 200
+    SC = _random_sc(N, 3)
+    rng = np.random.default_rng(8)
+    p = ops.make_params(N, 30, 4100, 80, P=0.4, rhoE=0.18, seed=5)                  # crosses an a_ie recombination (step 4096)
+    args = (p, SC, np.full(B, 0.16), rng.uniform(-0.1, 0.3, B), np.full(B, 7.68), rng.uniform(-0.2, 0.2, B))
+    kw = dict(mapG=rng.uniform(0.5, 1.5, N), mapS=rng.uniform(0.8, 1.2, N), streams=rng.integers(0, 2 ** 62, B).astype(np.uint64))
+    monkeypatch.setenv("NREM_BIG_PERSIST", "0")
+    E0, f0 = ops.big_integrate_f32(*args, **kw)
+    monkeypatch.setenv("NREM_BIG_PERSIST", "1")
+    E1, f1 = ops.big_integrate_f32(*args, **kw)
+    assert E0.shape == (4, N, B) and np.isfinite(f0).all()
+    assert np.array_equal(E0, E1) and np.array_equal(f0, f1)
+
+
 def test_large_connectome_matches_small_path_statistics(aal90):
     """The per-step kernel and the register-resident kernel integrate the same model with the same noise: on AAL90 (N = 90,
     which both accept) their float32 trajectories agree to rounding over a short horizon, incl. an a_ie recombination."""
@@ -536,3 +554,27 @@ def test_large_connectome_matches_small_path_statistics(aal90):
     E2, f2 = ops.big_integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=st, kernel="tc3")
     assert np.max(np.abs(E1[0] - E2[0]) / np.abs(E1[0])) < 5e-3          # 0.43 s of chaotic float32 dynamics
     assert np.max(np.abs(f1[2] - f2[2]) / np.abs(f1[2])) < 5e-3
+
+
+def test_large_connectome_argument_errors_and_ragged_batch(oracle_lib):
+    """Error behaviour at the C ABI (negative status -> NremError with the library's message) and a batch that is not a
+    multiple of the 128-simulation tile (padding simulations never leak into the outputs)."""
+    from nremmodfc_b200 import ops
+    from nremmodfc_b200._lib import NremError
+    from oracle import wc_oracle
+    N = 40
+    SC = _random_sc(N, 1)
+    p = ops.make_params(N, 5, 5, 20, P=0.4, rhoE=0.18, seed=3)
+    with pytest.raises(NremError):
+        ops.big_integrate_f32(ops.make_params(8, 5, 5, 20), _random_sc(8, 2), [0.16], [0.0], [7.68], [0.0])      # nnodes < 16
+    with pytest.raises(NremError):
+        ops.big_integrate_f32(p, SC, [0.16], [0.0], [7.68], [0.0], kernel="fma")                                   # no FMA variant
+    with pytest.raises(ValueError):
+        ops.big_integrate_f32(p, SC[:, :-1], [0.16], [0.0], [7.68], [0.0])
+    E, fin = ops.big_integrate_f32(p, SC, np.full(3, 0.16), [0.0, 0.1, 0.2], np.full(3, 7.68), [0.0, 0.0, -0.1],
+                                   streams=np.array([7, 8, 9], dtype=np.uint64), kernel="tc3")
+    assert E.shape == (1, N, 3) and fin.shape == (3, N, 3)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    for b, (g, s) in enumerate([(0.16, 7.68), (0.26, 7.68), (0.36, 7.58)]):
+        fo = oracle_lib.wc_run(SC, np.full(N, g), np.full(N, s), 5, 5, 20, seed=3, stream=7 + b, p=po, want="final")
+        assert np.max(np.abs(fin[:, :, b] - fo) / np.abs(fo)) < 2e-5
