@@ -320,9 +320,6 @@ static BatchConst make_const(const nrem_wc_params& p) {
     c.rE = (float)p.rE; c.rI = (float)p.rI; c.mu = (float)p.mu; c.sq = (float)p.sqdtD;
     c.kE = (float)(p.dtSim / p.tauE); c.kI = (float)(p.dtSim / p.tauI);
     c.sigI2 = (float)(-p.sigmaI * 1.4426950408889634);
-    c.cIE = c.a_ei * c.sigI2; c.cII = -c.a_ii * c.sigI2; c.cI0 = -c.mu * c.sigI2;
-    c.m2ln2s = -1.3862943611198906f * c.sq * c.sq;
-    c.Pmu = c.P - c.mu;
     c.E0 = (float)p.E0; c.I0 = (float)p.I0; c.a0 = (float)p.a_ie_0;
     c.k0 = (uint32_t)p.seed; c.k1 = (uint32_t)(p.seed >> 32);
     c.N = p.nnodes;
@@ -533,7 +530,6 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
     bool first = true;
     for (int ph = 0; ph < 3; ++ph) {
         A.kA = (float)(p.dtSim / p.tau_ip[ph]);
-        A.nkr = -A.kA * A.c.rhoE;
         for (int64_t i0 = 0; i0 < ns[ph]; i0 += chunk_steps) {
             const int64_t n = std::min(chunk_steps, ns[ph] - i0);
             A.step0 = (uint32_t)step; A.nsteps = (int)n; A.init = first ? 1 : 0;

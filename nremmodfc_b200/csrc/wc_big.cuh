@@ -362,15 +362,18 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 e[0] = S.Acur[idx]; e[1] = S.Acur[idx + kTile];
                 if (!MIXED) { e[NE - 2] = S.Acur[plane + idx]; e[NE - 1] = S.Acur[plane + idx + kTile]; }
             };
-            if (ng > 0) loadE(0, ce);
+            // software pipeline: the TMEM loads (coupling + xp) and the E(t) loads of group g + 1 are in flight while group g is computed
+            uint32_t cr[8], xp8[8], crn[8], xpn[8];
+            if (ng > 0) { loadE(0, ce); tmem_ld8(tmem_mine + kBigNT, xp8); }          // xp does not depend on the MMAs
             mbar_wait(accum, (uint32_t)(it & 1));
             tc_fence_after();
+            if (ng > 0) { tmem_ld8(tmem_mine, cr); tmem_ld_wait16(cr, xp8); }
             for (int g = 0; g < ng; ++g) {
-                if (g + 1 < ng) loadE(g + 1, ne);
-                uint32_t cr[8], xp8[8];
-                tmem_ld8(tmem_mine + 8 * g, cr);
-                tmem_ld8(tmem_mine + kBigNT + 8 * g, xp8);
-                tmem_ld_wait16(cr, xp8);
+                if (g + 1 < ng) {
+                    loadE(g + 1, ne);
+                    tmem_ld8(tmem_mine + 8 * (g + 1), crn);
+                    tmem_ld8(tmem_mine + kBigNT + 8 * (g + 1), xpn);
+                }
                 const int node0 = node_base + 8 * g;
                 const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
                 if (S.coup) {                    // test hook (first step only)
@@ -417,8 +420,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                         S.Anext[plane + idx + h * kTile] = make_float4(En[4 * h] - hi[0], En[4 * h + 1] - hi[1], En[4 * h + 2] - hi[2], En[4 * h + 3] - hi[3]);
                     }
                 }
+                if (g + 1 < ng) tmem_ld_wait16(crn, xpn);
 #pragma unroll
                 for (int k = 0; k < NE; ++k) ce[k] = ne[k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { cr[k] = crn[k]; xp8[k] = xpn[k]; }
             }
         }
             if (PERSIST) {

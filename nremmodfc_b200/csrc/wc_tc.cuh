@@ -230,12 +230,10 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const uint64_t bd_hi = umma_desc(smem_u32(Bh), kLBO_B, kSBO), bd_lo = umma_desc(smem_u32(Bl), kLBO_B, kSBO);
     float4* Ah4 = reinterpret_cast<float4*>(Ah);
     float4* Al4 = reinterpret_cast<float4*>(Al);
-    const float Pmu = c.Pmu;                             // constant part of the E sigmoid argument
-    const float nkr = A.nkr;
+    const float Pmu = c.P - c.mu;                        // constant part of the E sigmoid argument
+    const float nmu = -c.mu, nkr = -A.kA * c.rhoE;
     const float Gh = G0 + dG, sgh = sg0 + dsg;           // HOMO: map == 1 everywhere
-    const float two_pi = 6.2831853071795865f;
-    const float m2ln2s = c.m2ln2s;                       // radius already scaled by sqdtD: r = sqrt(-2 ln u) * sq
-    const float cIE = c.cIE, cII = c.cII, cI0 = c.cI0;   // I-sigmoid argument in ex2 units
+    const float two_pi = 6.2831853071795865f, m2ln2 = -1.3862943611198906f;
 
     // The step loop for a chunk with KN live nodes (KN = CH, or 18 for the last chunk of N = 90).
     auto run = [&](auto KNc) {
@@ -295,7 +293,8 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             auto node_pre = [&](int k) {
                 const float abk = (k & 3) == 0 ? ab4.x : (k & 3) == 1 ? ab4.y : (k & 3) == 2 ? ab4.z : ab4.w;
                 xp[k] = fmaf(-abk, I[k], fmaf(-a[k], I[k], fmaf(c.a_ee, E[k], xp[k])));
-                const float SI = rcpf(1.0f + ex2f(fmaf(cII, I[k], fmaf(cIE, E[k], cI0))));
+                const float y = fmaf(-c.a_ii, I[k], fmaf(c.a_ei, E[k], nmu));
+                const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
                 a[k] = fmaf(I[k], fmaf(E[k], A.kA, nkr), a[k]);
                 I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
             };
@@ -305,18 +304,18 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
                 const float l0 = lg2f(u23f(ph.x)), l1 = lg2f(u23f(ph.z));
                 const float a0 = fmaf(__uint_as_float(0x3f800000u | (ph.y >> 9)), two_pi, -1.49999994f * two_pi);
                 const float a1 = fmaf(__uint_as_float(0x3f800000u | (ph.w >> 9)), two_pi, -1.49999994f * two_pi);
-                const float r0 = sqrtaf(m2ln2s * l0), r1 = sqrtaf(m2ln2s * l1);
-                const float z0 = fmaf(r0, cosaf(a0), Pmu);
+                const float r0 = sqrtaf(m2ln2 * l0), r1 = sqrtaf(m2ln2 * l1);
+                const float z0 = r0 * cosaf(a0);
                 if (g + 1 < NQ) {
                     // PIPE != 0: A.zero is 0 at run time but opaque to ptxas, so the next quad's counter truly depends on a
                     // MUFU result of this quad (one LOP3 per quad) and its Philox rounds cannot be hoisted in front of it
                     const uint32_t ctr = PIPE == 0 ? step : (step ^ (__float_as_uint(PIPE == 1 ? l0 : z0) & A.zero));
                     ph = philox4x32_10(ctr, (uint32_t)(chunk * (CH / 4) + g + 1), s_lo, s_hi, c.k0, c.k1);
                 }
-                xp[4 * g + 0] = z0;
-                xp[4 * g + 1] = fmaf(r0, sinaf(a0), Pmu);
-                xp[4 * g + 2] = fmaf(r1, cosaf(a1), Pmu);
-                xp[4 * g + 3] = fmaf(r1, sinaf(a1), Pmu);
+                xp[4 * g + 0] = fmaf(c.sq, z0, Pmu);
+                xp[4 * g + 1] = fmaf(c.sq, r0 * sinaf(a0), Pmu);
+                xp[4 * g + 2] = fmaf(c.sq, r1 * cosaf(a1), Pmu);
+                xp[4 * g + 3] = fmaf(c.sq, r1 * sinaf(a1), Pmu);
                 ab4 = Ab4[(chunk * (CH / 4) + g) * kTile + simt];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
