@@ -75,6 +75,24 @@ def gather_rows(local_ids, local_rows, n_total, group=None):
     return out
 
 
+def shuffled_symmetric_maps(vec, K, seed):
+    """K hemisphere-mirrored shuffles of a per-node map, the rule of empirical/retrieve_AALmaps.py:62-75 (BASELINE configs[3],
+    "many shuffled maps"): the first half of the nodes is permuted at random and node N-1-i receives the value of node
+    N-1-perm[i], so homotopic regions stay paired.  Returns (maps [K, N], index [K, N]) from numpy.random.default_rng(seed)."""
+    vec = np.asarray(vec, dtype=np.float64)
+    N = vec.shape[0]
+    if N % 2:
+        raise ValueError("a hemisphere-mirrored shuffle needs an even number of nodes")
+    h = N // 2
+    rng = np.random.default_rng(seed)
+    idx = np.empty((K, N), dtype=np.int64)
+    for k in range(K):
+        perm = rng.permutation(h)
+        idx[k, :h] = perm
+        idx[k, N - 1 - np.arange(h)] = N - 1 - perm
+    return vec[idx], idx
+
+
 def pad_by_map(map_id):
     """Order/pad simulations so that every 128-tile holds one map id.
 

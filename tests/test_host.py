@@ -201,3 +201,23 @@ def test_c_abi_argument_errors(built):
     assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"nnodes <= 96" in lib.nrem_last_error()
     assert lib.nrem_sweep_run(None, *([one] * 7), None, one, one, one, one, None, None) == -1
     assert lib.nrem_selftest_tc_coupling(one, one, one, 2, 0, 0, 0, 0, 0, None) == -1
+
+
+def test_shuffled_symmetric_maps_follow_the_reference_rule(aal90):
+    """empirical/retrieve_AALmaps.py:62-75: left hemisphere permuted, right hemisphere mirrored.  The reference's own shuffled
+    VAChT map (committed fixture) satisfies exactly this relation to the unshuffled one."""
+    from nremmodfc_b200 import sweep
+    o, s = aal90["map_ACh"], aal90["map_ACh_shuf"]
+    perm = [int(np.argmin(np.abs(o[:45] - v))) for v in s[:45]]
+    assert sorted(perm) == list(range(45))
+    assert all(abs(s[89 - i] - o[89 - perm[i]]) < 1e-12 for i in range(45))
+    maps, idx = sweep.shuffled_symmetric_maps(o, 5, seed=3)
+    assert maps.shape == (5, 90) and idx.shape == (5, 90)
+    for k in range(5):
+        assert sorted(idx[k]) == list(range(90)) and sorted(idx[k, :45]) == list(range(45))
+        assert all(idx[k, 89 - i] == 89 - idx[k, i] for i in range(45))
+        assert np.array_equal(maps[k], o[idx[k]]) and abs(maps[k].mean() - o.mean()) < 1e-12
+    m2, _ = sweep.shuffled_symmetric_maps(o, 5, seed=3)
+    assert np.array_equal(maps, m2) and not np.array_equal(maps[0], maps[1])
+    with pytest.raises(ValueError):
+        sweep.shuffled_symmetric_maps(np.ones(7), 1, 0)
