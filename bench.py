@@ -318,10 +318,19 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the short large-connectome leg (configs[4])")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on communicator
+    # creation), so everything but our own print() goes to stderr: fd 1 is pointed at fd 2 and sys.stdout keeps the real one.
+    sys.stdout.flush()
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_out
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        real_out.flush()
 
 
 if __name__ == "__main__":
