@@ -70,6 +70,20 @@ __device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
                  :: "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// wait for three 8-column loads issued back to back (coupling, G_i, sigma_i)
+__device__ __forceinline__ void tmem_ld_wait24(uint32_t (&r)[8], uint32_t (&q)[8], uint32_t (&p)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                   "+r"(p[0]), "+r"(p[1]), "+r"(p[2]), "+r"(p[3]), "+r"(p[4]), "+r"(p[5]), "+r"(p[6]), "+r"(p[7])
+                 :: "memory");
+}
+
 // Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell).  Offsets in bytes.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
@@ -85,6 +99,8 @@ constexpr uint32_t kLBO_B = kTcN * 16;              // next 4-column group of B:
 constexpr uint32_t kABytes = (kTcK / 4) * kLBO_A;   // 49152
 constexpr uint32_t kBBytes = (kTcK / 4) * kLBO_B;   // 36864
 constexpr uint32_t kTmemCols = 128;                 // columns 0..95: coupling accumulator D
+constexpr uint32_t kTmemColsMaps = 512;             // heterogeneous maps: + columns 128..223 G_i, 256..351 sigma_i (per simulation, node)
+constexpr uint32_t kTmemG = 128, kTmemS = 256;
 constexpr uint32_t kRecombine = 4096;               // a_base <- a_base + delta at global steps that are multiples of this
 // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9 / 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
@@ -188,7 +204,8 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     for (int k = tid; k < (int)(kABytes / 4) * (SPLIT ? 2 : 1); k += NT) Ah[k] = 0.f;     // padding columns of A stay 0
     const int mid = A.tile_map[tile];
     if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
-    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+    constexpr bool MAPS_TMEM = !HOMO && CH == 24;       // per-node G_i, sigma_i parked in spare TMEM columns (see the E update)
+    if (warp == 0) tmem_alloc(tmem_slot, MAPS_TMEM ? kTmemColsMaps : kTmemCols);
     if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
     fence_proxy_async();                  // B tile (generic-proxy stores) -> visible to the tensor core's async proxy
     tc_fence_before();
@@ -226,6 +243,23 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
     const uint64_t strm = A.streams[sim];
     const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
+    if (MAPS_TMEM) {
+        // G_i = G0 + dG mapG_i and sigma_i (in ex2 units) are constant over the launch: one tcgen05.st per 8 nodes here replaces
+        // 2 LDS + 2 FFMA per node and Euler step; they come back with the coupling in the same tcgen05.wait::ld
+#pragma unroll
+        for (int h = 0; h < CH / 8; ++h) {
+            uint32_t g8[8], s8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int node = chunk * CH + 8 * h + j;
+                g8[j] = __float_as_uint(fmaf(dG, mG[node], G0));
+                s8[j] = __float_as_uint(fmaf(dsg, mS[node], sg0));
+            }
+            tmem_st8(tmem_mine + kTmemG + 8 * h, g8);
+            tmem_st8(tmem_mine + kTmemS + 8 * h, s8);
+        }
+        tmem_st_wait();
+    }
     const uint64_t ad_hi = umma_desc(smem_u32(Ah), kLBO_A, kSBO), ad_lo = umma_desc(smem_u32(Al), kLBO_A, kSBO);
     const uint64_t bd_hi = umma_desc(smem_u32(Bh), kLBO_B, kSBO), bd_lo = umma_desc(smem_u32(Bl), kLBO_B, kSBO);
     float4* Ah4 = reinterpret_cast<float4*>(Ah);
@@ -326,16 +360,22 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             tc_fence_after();
 #pragma unroll
             for (int h = 0; h < (KN + 7) / 8; ++h) {
-                uint32_t cr[8];
+                uint32_t cr[8], g8[8], s8[8];
                 if (8 * h + 8 <= CH) tmem_ld8(tmem_mine + 8 * h, cr); else tmem_ld4(tmem_mine + 8 * h, cr);
-                tmem_ld_wait8(cr);
+                if (MAPS_TMEM) {
+                    tmem_ld8(tmem_mine + kTmemG + 8 * h, g8);
+                    tmem_ld8(tmem_mine + kTmemS + 8 * h, s8);
+                    tmem_ld_wait24(cr, g8, s8);
+                } else {
+                    tmem_ld_wait8(cr);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int k = 8 * h + j;
                     if (k < KN) {
                         const int node = chunk * CH + k;
-                        const float Gi = HOMO ? Gh : fmaf(dG, mG[node], G0);
-                        const float sg2 = HOMO ? sgh : fmaf(dsg, mS[node], sg0);
+                        const float Gi = HOMO ? Gh : MAPS_TMEM ? __uint_as_float(g8[j]) : fmaf(dG, mG[node], G0);
+                        const float sg2 = HOMO ? sgh : MAPS_TMEM ? __uint_as_float(s8[j]) : fmaf(dsg, mS[node], sg0);
                         const float x = fmaf(Gi, __uint_as_float(cr[j]), xp[k]);
                         const float SE = rcpf(1.0f + ex2f(x * sg2));
                         E[k] = fmaf(c.kE, fmaf(fmaf(-c.rE, E[k], 1.0f), SE, -E[k]), E[k]);
@@ -355,7 +395,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, kTmemCols);
+    if (warp == 0) tmem_dealloc(tmem_d, MAPS_TMEM ? kTmemColsMaps : kTmemCols);
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
         const int node = chunk * CH + k;

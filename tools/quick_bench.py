@@ -16,14 +16,17 @@ B = tiles * 128
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 rng = np.random.default_rng(0)
 dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+hetero = os.environ.get("NREM_QB_HETERO", "0") != "0"       # heterogeneous NA/ACh maps (the map / shuffled modalities)
+mG = d["map_ACh"] / d["map_ACh"].mean() if hetero else None
+mS = d["map_NA"] / d["map_NA"].mean() if hetero else None
 for kern in sys.argv[3:] or ["fma", "tc", "tc3"]:
     for rec in (False, True):
         p = ops.make_params(90, 0, 0 if rec else steps, steps if rec else 0, P=0.4, rhoE=0.18, seed=1)
         try:
-            ops.integrate_f32(p, d["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, kernel=kern, record=False)  # warm
+            ops.integrate_f32(p, d["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, kernel=kern, record=False)  # warm
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            _, fin = ops.integrate_f32(p, d["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, kernel=kern, record=False)
+            _, fin = ops.integrate_f32(p, d["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, kernel=kern, record=False)
             torch.cuda.synchronize()
             dt = ops.last_integrate_ms() * 1e-3
         except Exception as e:  # noqa: BLE001
