@@ -303,10 +303,11 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             // 2. record E(t) (state BEFORE the update, netwWilsonCowanPlastic.py:129-130)
             if (A.rec) {
                 if (rc == 0) {
+                    // one base pointer per row, then a constant stride per node (LIGHT: N == 90, every node of the loop is live)
+                    float* dst = A.Ebuf + (row * N + chunk * CH) * A.Bs + sim;
 #pragma unroll
                     for (int k = 0; k < KN; ++k) {
-                        const int node = chunk * CH + k;
-                        if (node < N) A.Ebuf[(row * N + node) * A.Bs + sim] = E[k];
+                        if (LIGHT || chunk * CH + k < N) dst[(int64_t)k * A.Bs] = E[k];
                     }
                     ++row;
                 }
