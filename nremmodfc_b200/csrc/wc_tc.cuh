@@ -299,7 +299,17 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
             // (with LIGHT the issuer runs the 18-node copy of this loop: the 24-node copy carries no MMA code, -5.6 KB of hot
             // instruction footprint)
             if constexpr (!LIGHT || KN != CH) {
-                if (issuer) {
+                if (LIGHT) {
+                    // warp-uniform branch + elect.sync: ptxas then knows a single lane issues and moves the descriptors to uniform
+                    // registers once, instead of wrapping every tcgen05.mma in a lane-by-lane (BRA.U.ANY) loop
+                    if (warp == 4 * (NCHUNK - 1)) {
+                        if (elect_one()) {
+                            tc_fence_after();
+                            issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
+                        }
+                        __syncwarp();
+                    }
+                } else if (issuer) {
                     tc_fence_after();
                     issue_coupling<NPASS>(ad_hi, ad_lo, bd_hi, bd_lo, tmem_d, kIdescTf32, bar);
                 }
