@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     if (warp == 0) {
       uint32_t ring = 0;                                  // stages issued so far (continues across the steps of a persistent launch)
       for (int it = 0; it < nsteps; ++it) {
-        if (lane == 0) {
+        if (elect_one()) {      // (elect.sync under a warp-uniform branch: descriptors/addresses go to uniform registers once)
             // ---- producer: one contiguous bulk copy per operand and stage ----
             const float4* Acur = big_step_of(A, it, PERSIST).Acur;
             const char* a0 = reinterpret_cast<const char*>(Acur + (size_t)tile * A.KG * kTile);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     } else if (warp == 1) {
       uint32_t ring = 0;
       for (int it = 0; it < nsteps; ++it) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ---- MMA issuer ----
             const uint32_t base = smem_u32(smraw);
             uint32_t acc = 0;
