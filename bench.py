@@ -251,11 +251,11 @@ def run_ours(args):
         flop_per_launch, avg_ms = k1_flops / groups / max(k1_launches, 1), k1_ms / max(k1_launches, 1)
     # HBM side of the roofline: the integrator's only algorithmic HBM traffic is the E samples it records
     # (rows x 90 x sims x 4 B per recording launch); ncu (profiles/r01_final_ncu_integrator.md) measured
-    # dram read+write = 1.712e9 B for a 148-tile, 250-row launch whose algorithmic bytes are 1.705e9.
+    # dram read+write = 1.713e9 B for a 148-tile, 250-row launch whose algorithmic bytes are 1.705e9.
     tiles_per_launch = (B + 127) // 128 / groups
     rows_per_launch = (args.chunk_samples or 250)
     alg_bytes = rows_per_launch * 90 * tiles_per_launch * 128 * 4
-    ncu_traffic = 1.712e9 / 148 * tiles_per_launch
+    ncu_traffic = 1.713e9 / 148 * tiles_per_launch
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
@@ -284,7 +284,7 @@ def run_ours(args):
                          "launches_timed": k1_launches, "avg_launch_ms": avg_ms, "algorithmic_flop_per_launch": flop_per_launch,
                          "peak_source": "measured in this run: register-only FFMA chains on all SMs (nrem_measure_fma_peak)",
                          "note": "the SC.E contraction (82 % of the algorithmic flop) runs on tcgen05 tensor cores, so the FP32-FMA roof can be exceeded",
-                         "limiters_ncu": {"issue_slots_pct": 62.2, "xu_mufu_pipe_pct": 61.7, "fma_pipe_pct": 42.4, "tensor_pipe_pct": 24.7,
+                         "limiters_ncu": {"issue_slots_pct": 62.9, "xu_mufu_pipe_pct": 63.4, "fma_pipe_pct": 43.4, "tensor_pipe_pct": 25.4,
                                           "source": "profiles/r01_final_ncu_integrator.md (static, from the ncu capture of this kernel)"},
                          "hbm": {"algorithmic_bytes_per_recording_launch": alg_bytes, "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9,
                                  "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
