@@ -797,7 +797,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         // barrier.cluster per step, no launches).  Needs the cluster to fit the portable size and to be schedulable with this much
         // shared memory.  Correct (tests run both modes) but on B200 it measured 42.6-44.1 us/step against 41.3-42.2 for one launch
         // per step with programmatic dependent launch (tc3: 52-54 vs 47.7), so it is not the default.
-        bool persist = want_persist && slices <= 8 && total > 0;
+        bool persist = want_persist && slices <= 8 && total > 0 && total <= 0x7fffffff;    // nsteps is an int
         void (*kern_p)(const BigArgs) = pick2(std::true_type{});
         cudaLaunchConfig_t cfgp = {};
         cudaLaunchAttribute atp[1];
