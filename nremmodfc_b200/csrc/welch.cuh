@@ -79,11 +79,17 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
 }
 
 // FFT of one series in shared memory; returns the buffer holding the result.
+// `a` holds the output of the first pass (radix 4, done by the caller while loading) when FIRST_DONE, else the input.
+template <bool FIRST_DONE>
 __device__ __forceinline__ float2* fft_series(float2* a, float2* b, const WelchPlan& W, const float2* tw, int lane, int nlanes, bool active) {
     const int M = W.M;
     if (M == 2000) {                      // the reference's nperseg = 4000: radices 4,4,5,5,5 with compile-time strides
-        if (active) stockham_pass<4, 1>(a, b, M, 1, tw, lane, nlanes);
-        __syncthreads();
+        if (!FIRST_DONE) {
+            if (active) stockham_pass<4, 1>(a, b, M, 1, tw, lane, nlanes);
+            __syncthreads();
+        } else {
+            float2* t = a; a = b; b = t;  // the first pass already wrote into what we call b below
+        }
         if (active) stockham_pass<4, 4>(b, a, M, 4, tw, lane, nlanes);
         __syncthreads();
         if (active) stockham_pass<5, 16>(a, b, M, 16, tw, lane, nlanes);
@@ -94,8 +100,8 @@ __device__ __forceinline__ float2* fft_series(float2* a, float2* b, const WelchP
         __syncthreads();
         return b;
     }
-    int p = 1;
-    for (int st = 0; st < W.nstages; ++st) {
+    int p = FIRST_DONE ? W.radix[0] : 1;
+    for (int st = FIRST_DONE ? 1 : 0; st < W.nstages; ++st) {
         const int R = W.radix[st];
         if (active) {
             if (R == 4) stockham_pass<4, 0>(a, b, M, p, tw, lane, nlanes);
@@ -130,37 +136,58 @@ __global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const floa
     for (int k = tid; k < kWelchSims * (M + 1); k += kWelchThreads) pacc[k] = 0.f;
     for (int k = tid; k < M; k += kWelchThreads) tw[k] = W.tw[k];
     const int half = start / 2;                                          // start is even: pairs never straddle the wrap
+    const bool fuse4 = W.radix[0] == 4;                                  // first Stockham pass (radix 4, no twiddles) fused with the load
+    const float2* w2 = reinterpret_cast<const float2*>(W.window);
     for (int node = 0; node < N; ++node) {
-        __syncthreads();
+        __syncthreads();                                                  // the previous node's un-packing has read buf0/buf1
+        // Load + Hann window (+ first radix-4 pass).  detrend='constant' is applied in the frequency domain: the periodic Hann
+        // window's DFT is L/2 at k = 0, -L/4 at k = +-1 and 0 elsewhere, so removing the mean only changes bins 0 and 1.
         float sum = 0.f;
         if (active) {
             const float2* src = reinterpret_cast<const float2*>(wring + ((int64_t)node * Bs + s_base + sub) * L);
-            for (int n = lane; n < M; n += NL) {
-                int m = n + half;
-                if (m >= M) m -= M;
-                const float2 v = src[m];
-                buf0[sub * M + n] = v;
-                sum += v.x + v.y;
+            if (fuse4) {
+                const int t = M / 4;
+                float2* out = buf1 + sub * M;
+                for (int i = lane; i < t; i += NL) {
+                    float2 u[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int n = i + r * t;
+                        int m = n + half;
+                        if (m >= M) m -= M;
+                        const float2 v = src[m];
+                        const float2 w = w2[n];
+                        sum += v.x + v.y;
+                        u[r] = make_float2(v.x * w.x, v.y * w.y);
+                    }
+                    const float2 a = cadd(u[0], u[2]), bq = csub(u[0], u[2]), c = cadd(u[1], u[3]), d = csub(u[1], u[3]);
+                    float4* o4 = reinterpret_cast<float4*>(out + 4 * i);   // out[4 i + r], r = 0..3: two 16-byte stores
+                    const float2 x0 = cadd(a, c), x1 = make_float2(bq.x + d.y, bq.y - d.x);
+                    const float2 x2 = csub(a, c), x3 = make_float2(bq.x - d.y, bq.y + d.x);
+                    o4[0] = make_float4(x0.x, x0.y, x1.x, x1.y);
+                    o4[1] = make_float4(x2.x, x2.y, x3.x, x3.y);
+                }
+            } else {
+                for (int n = lane; n < M; n += NL) {
+                    int m = n + half;
+                    if (m >= M) m -= M;
+                    const float2 v = src[m];
+                    const float2 w = w2[n];
+                    sum += v.x + v.y;
+                    buf0[sub * M + n] = make_float2(v.x * w.x, v.y * w.y);
+                }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if ((tid & 31) == 0) red[tid >> 5] = sum;
+        if ((tid & 31) == 0) red[tid >> 5] = sum;                         // read after the FFT's barriers
         __syncthreads();
+        const float2* Z = fuse4 ? fft_series<true>(buf1 + sub * M, buf0 + sub * M, W, tw, lane, NL, active)
+                                : fft_series<false>(buf0 + sub * M, buf1 + sub * M, W, tw, lane, NL, active);
         float msum = 0.f;
 #pragma unroll
         for (int w = 0; w < WPS; ++w) msum += red[sub * WPS + w];
         const float mean = msum / (float)L;
-        if (active) {
-            const float2* w2 = reinterpret_cast<const float2*>(W.window);
-            for (int n = lane; n < M; n += NL) {                          // detrend='constant', Hann window
-                float2 v = buf0[sub * M + n];
-                const float2 w = w2[n];
-                buf0[sub * M + n] = make_float2((v.x - mean) * w.x, (v.y - mean) * w.y);
-            }
-        }
-        __syncthreads();
-        const float2* Z = fft_series(buf0 + sub * M, buf1 + sub * M, W, tw, lane, NL, active);
         // un-pack the real FFT: X[k] = (Z[k] + conj(Z[M-k]))/2 - i w^k (Z[k] - conj(Z[M-k]))/2,  w = exp(-2 pi i / L)
         if (active) {
             for (int k = lane; k <= M; k += NL) {
@@ -168,7 +195,10 @@ __global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const floa
                 const float2 ev = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
                 const float2 od = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
                 const float2 t = cmul(W.tw2[k], od);                      // -i * t = (t.y, -t.x)
-                const float xr = ev.x + t.y, xi = ev.y - t.x;
+                float xr = ev.x + t.y;
+                const float xi = ev.y - t.x;
+                if (k == 0) xr -= mean * (0.5f * (float)L);               // - mean * DFT(window)[0]
+                if (k == 1) xr += mean * (0.25f * (float)L);              // - mean * DFT(window)[1]
                 pacc[sub * (M + 1) + k] += (xr * xr + xi * xi) * ((k == 0 || k == M) ? 1.0f : 2.0f);
             }
         }
