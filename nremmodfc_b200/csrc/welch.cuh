@@ -79,25 +79,29 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
 }
 
 // FFT of one series in shared memory; returns the buffer holding the result.
+// The series of a CTA are independent: each has its own named barrier (ids 1..kWelchSims), so that the warps of one series never wait
+// for another series' pass.
+__device__ __forceinline__ void series_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // `a` holds the output of the first pass (radix 4, done by the caller while loading) when FIRST_DONE, else the input.
 template <bool FIRST_DONE>
-__device__ __forceinline__ float2* fft_series(float2* a, float2* b, const WelchPlan& W, const float2* tw, int lane, int nlanes, bool active) {
+__device__ __forceinline__ float2* fft_series(float2* a, float2* b, const WelchPlan& W, const float2* tw, int lane, int nlanes, bool active, int bar_id) {
     const int M = W.M;
     if (M == 2000) {                      // the reference's nperseg = 4000: radices 4,4,5,5,5 with compile-time strides
         if (!FIRST_DONE) {
             if (active) stockham_pass<4, 1>(a, b, M, 1, tw, lane, nlanes);
-            __syncthreads();
+            series_sync(bar_id, nlanes);
         } else {
             float2* t = a; a = b; b = t;  // the first pass already wrote into what we call b below
         }
         if (active) stockham_pass<4, 4>(b, a, M, 4, tw, lane, nlanes);
-        __syncthreads();
+        series_sync(bar_id, nlanes);
         if (active) stockham_pass<5, 16>(a, b, M, 16, tw, lane, nlanes);
-        __syncthreads();
+        series_sync(bar_id, nlanes);
         if (active) stockham_pass<5, 80>(b, a, M, 80, tw, lane, nlanes);
-        __syncthreads();
+        series_sync(bar_id, nlanes);
         if (active) stockham_pass<5, 400>(a, b, M, 400, tw, lane, nlanes);
-        __syncthreads();
+        series_sync(bar_id, nlanes);
         return b;
     }
     int p = FIRST_DONE ? W.radix[0] : 1;
@@ -110,7 +114,7 @@ __device__ __forceinline__ float2* fft_series(float2* a, float2* b, const WelchP
         }
         p *= R;
         float2* t = a; a = b; b = t;
-        __syncthreads();
+        series_sync(bar_id, nlanes);
     }
     return a;
 }
@@ -138,8 +142,9 @@ __global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const floa
     const int half = start / 2;                                          // start is even: pairs never straddle the wrap
     const bool fuse4 = W.radix[0] == 4;                                  // first Stockham pass (radix 4, no twiddles) fused with the load
     const float2* w2 = reinterpret_cast<const float2*>(W.window);
+    __syncthreads();                                                      // pacc and the twiddle table are set up by all threads
     for (int node = 0; node < N; ++node) {
-        __syncthreads();                                                  // the previous node's un-packing has read buf0/buf1
+        series_sync(1 + sub, NL);                                                  // the previous node's un-packing has read buf0/buf1
         // Load + Hann window (+ first radix-4 pass).  detrend='constant' is applied in the frequency domain: the periodic Hann
         // window's DFT is L/2 at k = 0, -L/4 at k = +-1 and 0 elsewhere, so removing the mean only changes bins 0 and 1.
         float sum = 0.f;
@@ -181,9 +186,9 @@ __global__ void __launch_bounds__(kWelchThreads) welch_segment_kernel(const floa
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         if ((tid & 31) == 0) red[tid >> 5] = sum;                         // read after the FFT's barriers
-        __syncthreads();
-        const float2* Z = fuse4 ? fft_series<true>(buf1 + sub * M, buf0 + sub * M, W, tw, lane, NL, active)
-                                : fft_series<false>(buf0 + sub * M, buf1 + sub * M, W, tw, lane, NL, active);
+        series_sync(1 + sub, NL);
+        const float2* Z = fuse4 ? fft_series<true>(buf1 + sub * M, buf0 + sub * M, W, tw, lane, NL, active, 1 + sub)
+                                : fft_series<false>(buf0 + sub * M, buf1 + sub * M, W, tw, lane, NL, active, 1 + sub);
         float msum = 0.f;
 #pragma unroll
         for (int w = 0; w < WPS; ++w) msum += red[sub * WPS + w];
