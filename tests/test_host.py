@@ -221,3 +221,35 @@ def test_shuffled_symmetric_maps_follow_the_reference_rule(aal90):
     assert np.array_equal(maps, m2) and not np.array_equal(maps[0], maps[1])
     with pytest.raises(ValueError):
         sweep.shuffled_symmetric_maps(np.ones(7), 1, 0)
+
+
+def test_many_seeds_batch_assembly(monkeypatch, aal90):
+    """run_many_seeds.py:105-136 as one batch: (seed, state) order of itertools.product, per-state optima of :34-47, maps normalised
+    to mean 1, unique stream ids, and the reference's record layout — checked on the host with the GPU call replaced."""
+    from nremmodfc_b200 import many_seeds, sweep
+    seen = {}
+
+    def fake_sweep_gof(p, CM, emp, G0, dG, s0, ds, streams, mapG=None, mapS=None, want_fc=False, **kw):
+        seen.update(G0=G0, dG=dG, s0=s0, ds=ds, streams=streams, mapG=mapG, mapS=mapS, want_fc=want_fc, kw=kw)
+        rng = np.random.default_rng(0)
+        fc = rng.uniform(-0.2, 0.9, (len(G0), 90, 90))
+        fc = (fc + fc.transpose(0, 2, 1)) / 2
+        for f in fc:
+            np.fill_diagonal(f, 1.0)
+        return {"fc": fc}
+
+    monkeypatch.setattr(sweep, "sweep_gof", fake_sweep_gof)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    save = many_seeds.run_many_seeds(None, aal90["SC"], emp, aal90["map_ACh"], aal90["map_NA"], modality="map", seeds=range(3), Neq=7)
+    assert list(save) == [(s, st) for s in range(3) for st in ("W", "N1", "N2", "N3")]
+    assert seen["want_fc"] and seen["kw"] == {"Neq": 7}
+    opt = many_seeds.OPTIMALS["map"]
+    assert np.allclose(seen["G0"], 0.16) and np.allclose(seen["s0"], 7.68)
+    assert np.allclose(seen["dG"], [opt[st][1] for _ in range(3) for st in ("W", "N1", "N2", "N3")])
+    assert np.allclose(seen["ds"], [opt[st][3] for _ in range(3) for st in ("W", "N1", "N2", "N3")])
+    assert abs(seen["mapG"].mean() - 1) < 1e-12 and abs(seen["mapS"].mean() - 1) < 1e-12 and seen["mapG"].shape == (1, 90)
+    assert len(set(int(x) for x in seen["streams"])) == 12
+    rec = save[(1, "N2")]
+    assert set(rec) == {"Hin_sim", "Hse_sim", "Hin_node_sim", "Hse_node_sim", "sFC"}
+    assert rec["sFC"].min() >= 0.0 and rec["Hin_node_sim"].shape == (90,)           # HMA clips negatives in place, as the reference does
+    assert many_seeds.OPTIMALS["homo"]["N3"] == (0.16, -0.04, 7.68, 0.04) and many_seeds.OPTIMALS["shuf"]["N1"] == (0.16, 0.0, 7.68, 0.04)
