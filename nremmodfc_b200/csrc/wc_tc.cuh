@@ -162,10 +162,10 @@ constexpr int tc_smem_bytes() { return (NPASS == 3 ? 2 : 1) * (int)(kABytes + kB
 // HOMO : homogeneous sweep (every map entry is 1, so G_i and sigma_i are per-simulation scalars: -2 FMA, -2 LDS per
 //        node-step).  Constants (-mu, -kA*rhoE) are folded into the FMAs.
 // LIGHT: N == 90 only.  The last node chunk (nodes 72..95) holds 18 real nodes and 6 padding nodes; its warps run a
-//        second copy of the step loop compiled for 18 nodes, and the MMA issuer is a thread of that chunk, so the
-//        ~900 clk it spends issuing 36 tcgen05.mma per step are taken from the padding slack instead of making the
-//        other 15 warps wait at the CTA barrier (ncu: 11.7 % of all samples were that wait); the per-step CTA barrier is
-//        split into bar.arrive (workers) / bar.sync (issuer warp).
+//        second copy of the step loop compiled for 18 nodes, and the MMA issuer is the first warp of that chunk (one lane
+//        chosen by elect.sync), so the issue of the 36 tcgen05.mma per step is taken from the padding slack instead of
+//        making the other 15 warps wait at the CTA barrier (ncu: 11.7 % of all samples were that wait); the per-step CTA
+//        barrier is split into bar.arrive (workers) / bar.sync (issuer warp).  The 24-node copy carries no issue code.
 // a_ie : the plasticity increment dtSim/tau_ip * I (E - rhoE) is ~5e-7 per step while a_ie is 2.5..10, i.e. about ONE
 //        float32 ulp: accumulated directly in float32 the homeostatic loop loses the small corrections (measured: the
 //        homogeneous high-G cells of the full sweep drift off the reference's table).  So a_ie = a_base + delta: a_base
