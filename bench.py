@@ -284,7 +284,7 @@ def run_ours(args):
                          "launches_timed": k1_launches, "avg_launch_ms": avg_ms, "algorithmic_flop_per_launch": flop_per_launch,
                          "peak_source": "measured in this run: register-only FFMA chains on all SMs (nrem_measure_fma_peak)",
                          "note": "the SC.E contraction (82 % of the algorithmic flop) runs on tcgen05 tensor cores, so the FP32-FMA roof can be exceeded",
-                         "limiters_ncu": {"issue_slots_pct": 62.9, "xu_mufu_pipe_pct": 63.4, "fma_pipe_pct": 43.4, "tensor_pipe_pct": 25.4,
+                         "limiters_ncu": {"issue_slots_pct": 62.9, "xu_mufu_pipe_pct": 64.9, "fma_pipe_pct": 42.7, "tensor_pipe_pct": 26.0,
                                           "source": "profiles/r01_final_ncu_integrator.md (static, from the ncu capture of this kernel)"},
                          "hbm": {"algorithmic_bytes_per_recording_launch": alg_bytes, "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9,
                                  "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
