@@ -247,7 +247,9 @@ def run_ours(args):
         achieved, timing, share = k1_flops / (k1_ms * 1e-3) / 1e12, "CUDA events around every integrator launch", k1_ms / dev_ms
         flop_per_launch, avg_ms = k1_flops / max(k1_launches, 1), k1_ms / max(k1_launches, 1)
     else:                # tile groups overlap on the device: charge the integrator with the WHOLE step (lower bound)
-        achieved, timing, share = k1_flops / (dev_ms * 1e-3) / 1e12, f"{groups} tile-group streams overlap; whole-step device time charged", None
+        # share: fraction of tile group 0's stream time spent inside its integrator launches (CUDA events around each of them;
+        # the rest is that group's BOLD/filter launches and the FC/GoF tail) -- all groups run the same sequence
+        achieved, timing, share = k1_flops / (dev_ms * 1e-3) / 1e12, f"{groups} tile-group streams overlap; whole-step device time charged", k1_ms / dev_ms
         flop_per_launch, avg_ms = k1_flops / groups / max(k1_launches, 1), k1_ms / max(k1_launches, 1)
     # HBM side of the roofline: the integrator's only algorithmic HBM traffic is the E samples it records
     # (rows x 90 x sims x 4 B per recording launch); ncu (profiles/r01_final_ncu_integrator.md) measured
