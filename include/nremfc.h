@@ -71,6 +71,14 @@ int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, 
                     const uint64_t* streams, const double* noise, int noise_batch, int B, int64_t nrec,
                     double* Y, double* final_state, void* stream);
 
+/* Same with per-node vectors for the scalar model parameters ("Any of them can be redefined as a vector of length nnodes",
+ * netwWilsonCowanPlastic.py:21).  node_params: NULL or [NREM_NODE_PARAMS, N] (device) in the order
+ * a_ee, a_ei, a_ii, tauE, tauI, P, rhoE, rE, rI, mu, sigmaI; row k overrides the scalar of `p` for every node.       */
+#define NREM_NODE_PARAMS 11
+int nrem_wc_run_f64_ex(const nrem_wc_params* p, const double* CM, const double* G, const double* sigmaE,
+                       const double* node_params, const uint64_t* streams, const double* noise, int noise_batch, int B,
+                       int64_t nrec, double* Y, double* final_state, void* stream);
+
 /* Replaces wilsonCowan(t, X, sigmaE, mu, tau_ip, G) (netwWilsonCowanPlastic.py:77-83): one
  * derivative evaluation.  X [3,N], noise [N] (scaled), G/sigmaE [N] -> dX [3,N].            */
 int nrem_wc_derivative_f64(const nrem_wc_params* p, const double* CM, const double* X, const double* G,

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnremfc.so")
 
 ABI_SYMBOLS = [
-    "nrem_abi_version", "nrem_last_error", "nrem_device_count", "nrem_wc_run_f64", "nrem_wc_derivative_f64",
+    "nrem_abi_version", "nrem_last_error", "nrem_device_count", "nrem_wc_run_f64", "nrem_wc_run_f64_ex", "nrem_wc_derivative_f64",
     "nrem_bold_sim_f64", "nrem_filt_scratch_bytes", "nrem_filtfilt_decimate_f64", "nrem_fc_f64", "nrem_gof_f64", "nrem_kuramoto_f64",
     "nrem_sweep_create", "nrem_sweep_destroy", "nrem_sweep_device_bytes", "nrem_sweep_run",
     "nrem_sweep_integrate_f32", "nrem_big_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
@@ -50,6 +50,7 @@ lib.nrem_launch_count.restype = _i64
 lib.nrem_last_integrate_ms.restype = _d
 lib.nrem_launch_count.argtypes = [_i]
 lib.nrem_wc_run_f64.argtypes = [C.POINTER(WCParams), _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]
+lib.nrem_wc_run_f64_ex.argtypes = [C.POINTER(WCParams), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]
 lib.nrem_wc_derivative_f64.argtypes = [C.POINTER(WCParams), _vp, _vp, _vp, _vp, _vp, _d, _vp, _vp]
 lib.nrem_bold_sim_f64.argtypes = [_vp, _i, _i64, _i, _d, _vp, _vp]
 lib.nrem_filt_scratch_bytes.restype = _i64

@@ -147,6 +147,12 @@ static int check_params(const nrem_wc_params* p) {
 int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, const double* sigmaE,
                     const uint64_t* streams, const double* noise, int noise_batch, int B, int64_t nrec,
                     double* Y, double* final_state, void* stream) {
+    return nrem_wc_run_f64_ex(p, CM, G, sigmaE, nullptr, streams, noise, noise_batch, B, nrec, Y, final_state, stream);
+}
+
+int nrem_wc_run_f64_ex(const nrem_wc_params* p, const double* CM, const double* G, const double* sigmaE, const double* node_params,
+                       const uint64_t* streams, const double* noise, int noise_batch, int B, int64_t nrec,
+                       double* Y, double* final_state, void* stream) {
     if (int rc = check_params(p)) return rc;
     NREM_REQUIRE(CM && G && sigmaE, "CM, G and sigmaE are required");
     NREM_REQUIRE(B >= 1, "B must be positive");
@@ -154,7 +160,7 @@ int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, 
     NREM_REQUIRE(!noise || noise_batch == 1 || noise_batch == B, "noise_batch must be 1 or B");
     NREM_REQUIRE(!Y || nrec >= 1, "nrec must be positive when Y is given");
     WcF64Args A;
-    A.p = *p; A.CM = CM; A.G = G; A.sg = sigmaE; A.streams = streams; A.noise = noise;
+    A.p = *p; A.CM = CM; A.G = G; A.sg = sigmaE; A.streams = streams; A.noise = noise; A.node_par = node_params;
     A.noise_batch = noise ? noise_batch : 1; A.nrec = nrec; A.Y = Y; A.fin = final_state;
     const int N = p->nnodes;
     const int threads = (int)round_up(N, 32);

@@ -16,6 +16,7 @@ struct WcF64Args {
     const double* sg;
     const uint64_t* streams;
     const double* noise;
+    const double* node_par;     // NULL, or [NREM_NODE_PARAMS][N] per-node overrides of the scalar parameters (include/nremfc.h)
     int noise_batch;
     int64_t nrec;
     double* Y;
@@ -27,7 +28,7 @@ __device__ __forceinline__ double sigm(double x, double sigma, double mu) { retu
 // dynamic smem: Es[2][N] then (CM_SMEM) CMt[N][N] with CMt[j*N+i] = CM[i][j]; otherwise A.CM already IS the transpose
 // (global memory, coalesced over i)
 template <bool CM_SMEM>
-__global__ void wc_run_f64_kernel(const WcF64Args A) {
+__global__ void __launch_bounds__(CM_SMEM ? 256 : 1024) wc_run_f64_kernel(const WcF64Args A) {
     extern __shared__ double sm64[];
     const nrem_wc_params& p = A.p;
     const int N = p.nnodes;
@@ -43,6 +44,10 @@ __global__ void wc_run_f64_kernel(const WcF64Args A) {
     }
     const bool live = i < N;
     double E = p.E0, I = p.I0, a = p.a_ie_0;
+    // "Any of them can be redefined as a vector of length nnodes" (netwWilsonCowanPlastic.py:21)
+    auto npar = [&](int k, double scalar) { return (A.node_par && live) ? A.node_par[(size_t)k * N + i] : scalar; };
+    const double a_ee = npar(0, p.a_ee), a_ei = npar(1, p.a_ei), a_ii = npar(2, p.a_ii), tauE = npar(3, p.tauE), tauI = npar(4, p.tauI);
+    const double Pn = npar(5, p.P), rhoE = npar(6, p.rhoE), rE = npar(7, p.rE), rI = npar(8, p.rI), mu = npar(9, p.mu), sigmaI = npar(10, p.sigmaI);
     const double G = live ? A.G[(size_t)b * N + i] : 0.0;
     const double sg = live ? A.sg[(size_t)b * N + i] : 1.0;
     const uint64_t strm = A.streams ? A.streams[b] : (uint64_t)b;
@@ -97,9 +102,9 @@ __global__ void wc_run_f64_kernel(const WcF64Args A) {
                     sincos(ang, &sn, &cs);
                     nz = p.sqdtD * rad * ((i & 1) ? sn : cs);
                 }
-                const double dE = (-E + (1 - p.rE * E) * sigm(p.a_ee * E - a * I + G * coup + p.P + nz, sg, p.mu)) / p.tauE;
-                const double dI = (-I + (1 - p.rI * I) * sigm(p.a_ei * E - p.a_ii * I, p.sigmaI, p.mu)) / p.tauI;
-                const double da = (I * (E - p.rhoE)) / tau_ip;
+                const double dE = (-E + (1 - rE * E) * sigm(a_ee * E - a * I + G * coup + Pn + nz, sg, mu)) / tauE;
+                const double dI = (-I + (1 - rI * I) * sigm(a_ei * E - a_ii * I, sigmaI, mu)) / tauI;
+                const double da = (I * (E - rhoE)) / tau_ip;
                 E += p.dtSim * dE;
                 I += p.dtSim * dI;
                 a += p.dtSim * da;

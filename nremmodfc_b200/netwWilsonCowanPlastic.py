@@ -11,7 +11,8 @@ Differences (all supersets of the reference behaviour):
   * ``sid`` really seeds the noise: the stream is counter-based Philox keyed by (sid, replicate),
     so two calls with the same ``sid`` give the same trajectory.  (The reference's ``sid`` never
     reached numba's generator.)  Set ``noise`` to an array [steps, N] to inject a stream instead;
-  * only ``G`` and ``sigmaE`` may be length-N vectors (the only ones the drivers vary per node).
+  * ``run()`` takes a length-N vector for any node parameter (reference line 21); the batched sweep (``sweep.SweepPlan``)
+    takes per-node ``G`` and ``sigmaE``, the only ones the drivers vary per node.
 """
 import gc
 
@@ -68,12 +69,24 @@ def S(x, sigma, mu):
     return 1 / (1 + np.exp(-(np.asarray(x, dtype=np.float64) - mu) * sigma))
 
 
+def _node_vectors(nn):
+    """Attributes that were redefined as length-N vectors (reference line 21) -> {name: vector}."""
+    g = globals()
+    out = {}
+    for name in ops.NODE_PARAMS:
+        v = np.asarray(g[name], dtype=np.float64)
+        if v.ndim == 1 and v.shape[0] == nn:
+            out[name] = v
+        elif v.ndim != 0:
+            raise ValueError(f"{name} must be a scalar or a vector of length {nn}, got shape {v.shape}")
+    return out
+
+
 def _params(n1, n2, n3, nn):
     g = globals()
-    return ops.make_params(nn, n1, n2, n3, a_ee=g["a_ee"], a_ie_0=g["a_ie_0"], a_ei=g["a_ei"], a_ii=g["a_ii"],
-                           tauE=g["tauE"], tauI=g["tauI"], P=g["P"], rhoE=g["rhoE"], rE=g["rE"], rI=g["rI"],
-                           mu=g["mu"], sigmaI=g["sigmaI"], dtSim=g["dtSim"], sqdtD=g["sqdtD"],
-                           downsamp=int(g["dt"] / g["dtSim"]), seed=int(g["sid"]))
+    sc = {name: float(np.mean(g[name])) for name in ops.NODE_PARAMS}        # vectors travel separately (_node_vectors)
+    return ops.make_params(nn, n1, n2, n3, a_ie_0=g["a_ie_0"], dtSim=g["dtSim"], sqdtD=g["sqdtD"],
+                           downsamp=int(g["dt"] / g["dtSim"]), seed=int(g["sid"]), **sc)
 
 
 class _Recompilable:
@@ -90,7 +103,7 @@ class _Run(_Recompilable):
         nn = len(cm)
         p = _params(len(g["timeTrans1"]), len(g["timeTrans2"]), len(g["timeSim"]), nn)
         Y, _ = ops.wc_run(p, cm, g["G"], g["sigmaE"], B=1, streams=[int(g["replicate"])], noise=g["noise"],
-                          nrec=len(g["time"]), want_Y=True)
+                          nrec=len(g["time"]), want_Y=True, node_params=_node_vectors(nn) or None)
         return Y[0]
 
 

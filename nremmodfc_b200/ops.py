@@ -36,7 +36,7 @@ def make_params(nnodes, n1, n2, n3, **over):
             p.seed = int(v) & 0xFFFFFFFFFFFFFFFF
         else:
             if np.ndim(v) != 0:
-                raise ValueError(f"{k} must be a scalar on the GPU path (only G and sigmaE may be per-node)")
+                raise ValueError(f"{k} must be a scalar in nrem_wc_params (per-node vectors: node_params of wc_run; G and sigmaE everywhere)")
             setattr(p, k, float(v))
     p.nnodes, p.n1, p.n2, p.n3 = int(nnodes), int(n1), int(n2), int(n3)
     return p
@@ -88,9 +88,14 @@ def _per_node(x, B, N, name):
     return np.ascontiguousarray(a)
 
 
-def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=True, device=None):
+NODE_PARAMS = ("a_ee", "a_ei", "a_ii", "tauE", "tauI", "P", "rhoE", "rE", "rI", "mu", "sigmaI")     # NREM_NODE_PARAMS order
+
+
+def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=True, node_params=None, device=None):
     """run() of netwWilsonCowanPlastic.py:86-137 for B simulations (float64).
 
+    node_params: optional {name: length-N vector} for any of NODE_PARAMS ("Any of them can be redefined as a vector of
+    length nnodes", netwWilsonCowanPlastic.py:21); names not given keep the scalar of `p`.
     Returns (Y [B, nrec, 3, N] or None, final [B, 3, N])."""
     dev = _device(device)
     N = p.nnodes
@@ -111,13 +116,25 @@ def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=Tr
             raise ValueError(f"noise must be [1 or {B}, {steps}, {N}], got {noise.shape}")
         nb = noise.shape[0]
         d_noise = to_device(noise, torch.float64, dev)
+    npar = None
+    if node_params:
+        unknown = set(node_params) - set(NODE_PARAMS)
+        if unknown:
+            raise ValueError(f"not per-node parameters: {sorted(unknown)} (allowed: {NODE_PARAMS})")
+        npar = np.empty((len(NODE_PARAMS), N))
+        for k, name in enumerate(NODE_PARAMS):
+            v = np.asarray(node_params.get(name, getattr(p, name)), dtype=np.float64)
+            if v.ndim > 1 or (v.ndim == 1 and v.shape[0] != N):
+                raise ValueError(f"{name} must be a scalar or a vector of length {N}")
+            npar[k] = v
     with torch.cuda.device(dev):
         d_CM, d_G, d_sg = (to_device(x, torch.float64, dev) for x in (CM, G, sg))
+        d_np = None if npar is None else to_device(npar, torch.float64, dev)
         d_st = _u64(np.arange(B) if streams is None else streams, dev)
         d_Y = torch.empty((B, max(nrec, 1), 3, N), dtype=torch.float64, device=dev) if want_Y and nrec > 0 else None
         d_fin = torch.empty((B, 3, N), dtype=torch.float64, device=dev)
-        check(lib.nrem_wc_run_f64(C.byref(p), _ptr(d_CM), _ptr(d_G), _ptr(d_sg), _ptr(d_st), _ptr(d_noise), nb, B,
-                                  nrec, _ptr(d_Y), _ptr(d_fin), _stream()))
+        check(lib.nrem_wc_run_f64_ex(C.byref(p), _ptr(d_CM), _ptr(d_G), _ptr(d_sg), _ptr(d_np), _ptr(d_st), _ptr(d_noise), nb, B,
+                                     nrec, _ptr(d_Y), _ptr(d_fin), _stream()))
         Y = d_Y.cpu().numpy() if d_Y is not None else None
         return Y, d_fin.cpu().numpy()
 

@@ -578,3 +578,46 @@ def test_large_connectome_argument_errors_and_ragged_batch(oracle_lib):
     for b, (g, s) in enumerate([(0.16, 7.68), (0.26, 7.68), (0.36, 7.58)]):
         fo = oracle_lib.wc_run(SC, np.full(N, g), np.full(N, s), 5, 5, 20, seed=3, stream=7 + b, p=po, want="final")
         assert np.max(np.abs(fin[:, :, b] - fo) / np.abs(fo)) < 2e-5
+
+
+def test_every_node_parameter_as_a_vector(aal90):
+    """"Any of them can be redefined as a vector of length nnodes" (netwWilsonCowanPlastic.py:21): the float64 path takes per-node
+    vectors for all eleven node parameters; checked against the NumPy oracle (whose expressions broadcast) and through the drop-in
+    module surface."""
+    from nremmodfc_b200 import ops
+    from nremmodfc_b200 import netwWilsonCowanPlastic as wc
+    from oracle import wc_oracle
+    rng = np.random.default_rng(21)
+    N = 90
+    vec = {"a_ee": 3.5 + 0.2 * rng.random(N), "a_ei": 3.75 - 0.2 * rng.random(N), "a_ii": 0.1 * rng.random(N),
+           "tauE": 0.010 * (1 + 0.1 * rng.random(N)), "tauI": 0.020 * (1 + 0.1 * rng.random(N)), "P": 0.4 + 0.05 * rng.random(N),
+           "rhoE": 0.18 + 0.02 * rng.random(N), "rE": 0.5 + 0.05 * rng.random(N), "rI": 0.5 - 0.05 * rng.random(N),
+           "mu": 1.0 + 0.05 * rng.random(N), "sigmaI": 4.0 + 0.3 * rng.random(N)}
+    n1, n2, n3 = 50, 100, 200
+    p = ops.make_params(N, n1, n2, n3, seed=8)
+    G, sg = 0.16 + 0.05 * rng.random(N), 7.68 + 0.2 * rng.random(N)
+    Y, fin = ops.wc_run(p, aal90["SC"], G, sg, B=1, streams=[5], node_params=vec)
+    po = wc_oracle.params(**vec)
+    Yo, fo = wc_oracle.run(aal90["SC"], G, sg, n1, n2, n3, seed=8, streams=[5], p=po, return_final=True)
+    assert np.max(np.abs(Y[0] - Yo[0]) / np.abs(Yo[0])) < 1e-9 and np.max(np.abs(fin[0] - fo[0]) / np.abs(fo[0])) < 1e-9
+    # a subset of names keeps the scalars of p for the others; it must differ from the all-scalar run
+    Y1, _ = ops.wc_run(p, aal90["SC"], G, sg, B=1, streams=[5], node_params={"P": vec["P"]})
+    Y0, _ = ops.wc_run(p, aal90["SC"], G, sg, B=1, streams=[5])
+    assert not np.allclose(Y1, Y0) and not np.allclose(Y1, Y)
+    with pytest.raises(ValueError):
+        ops.wc_run(p, aal90["SC"], G, sg, node_params={"G0": vec["P"]})
+    with pytest.raises(ValueError):
+        ops.wc_run(p, aal90["SC"], G, sg, node_params={"P": vec["P"][:7]})
+    # drop-in surface: module attributes redefined as vectors
+    saved = {k: getattr(wc, k) for k in list(vec) + ["CM", "G", "sigmaE", "sid", "replicate", "timeTrans1", "timeTrans2", "timeSim", "time"]}
+    try:
+        for k, v in vec.items():
+            setattr(wc, k, v)
+        wc.CM, wc.G, wc.sigmaE, wc.sid, wc.replicate = aal90["SC"], G, sg, 8, 5
+        wc.timeTrans1, wc.timeTrans2, wc.timeSim = np.arange(n1), np.arange(n2), np.arange(n3)
+        wc.time = np.arange((n3 + 19) // 20)
+        Yd = wc.run()
+    finally:
+        for k, v in saved.items():
+            setattr(wc, k, v)
+    assert np.array_equal(Yd, Y[0])
