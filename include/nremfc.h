@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define NREM_ABI_VERSION 1
+#define NREM_ABI_VERSION 2
 
 typedef enum nrem_status {
     NREM_OK = 0,
@@ -73,8 +73,8 @@ int nrem_wc_run_f64(const nrem_wc_params* p, const double* CM, const double* G, 
 
 /* Same with per-node vectors for the scalar model parameters ("Any of them can be redefined as a vector of length nnodes",
  * netwWilsonCowanPlastic.py:21).  node_params: NULL or [NREM_NODE_PARAMS, N] (device) in the order
- * a_ee, a_ei, a_ii, tauE, tauI, P, rhoE, rE, rI, mu, sigmaI; row k overrides the scalar of `p` for every node.       */
-#define NREM_NODE_PARAMS 11
+ * a_ee, a_ei, a_ii, tauE, tauI, P, rhoE, rE, rI, mu, sigmaI, a_ie_0; row k overrides the scalar of `p` for every node. */
+#define NREM_NODE_PARAMS 12
 int nrem_wc_run_f64_ex(const nrem_wc_params* p, const double* CM, const double* G, const double* sigmaE,
                        const double* node_params, const uint64_t* streams, const double* noise, int noise_batch, int B,
                        int64_t nrec, double* Y, double* final_state, void* stream);
@@ -132,8 +132,8 @@ typedef struct nrem_sweep_opts {
     int64_t bold_downsamp;   /* decimation after filtering (reference: 1000)                         */
     double  bold_dt;         /* BOLD Euler step (reference: dt*downsamp = 0.04)                      */
     double  b[5], a[5];      /* band-pass coefficients, SciPy order                                  */
-    int32_t welch_nperseg;   /* 0 = no spectrum; else segment length of signal.welch (reference: 4000; even,   */
-                             /* nperseg/2 = 2^a 5^b <= 2560, multiple of 2*chunk_samples); 50 % overlap, Hann   */
+    int32_t welch_nperseg;   /* 0 = no spectrum; else segment length of signal.welch (reference: 4000): even, <= T,     */
+                             /* nperseg/2 = 2^a 5^b <= 2560 and nperseg/2 a multiple of chunk_samples; 50 % overlap, Hann */
     int32_t reserved;
     double  welch_fs;        /* sampling rate of the stored samples, 1/dt (reference: 500 Hz)                 */
 } nrem_sweep_opts;
@@ -147,17 +147,42 @@ int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan);
  *   CM [N,N] f64; mapG,mapS [n_maps,N] f64; G0,dG,sigma0,dsigma [B] f64; h_map_id [B] i32 (HOST pointer, may be NULL = all 0);
  *   streams [B] u64; emp [K,N,N] f64
  *   gof [B,K,4] f64; extra [B,4] f64 = (mean FC, sync, meta, peakfreq) — the last four columns of the reference's
- *   output row (whole_sweep_both.py:90-96); peakfreq is NaN unless opts.welch_nperseg > 0;
- *   fc NULL or [B,N,N] f64.
- * Returns after the last kernel has been enqueued on `stream`.                                 */
+ *   output row (whole_sweep_both.py:90-96); peakfreq is NaN unless opts.welch_nperseg > 0, sync/meta are NaN when the
+ *   decimated BOLD has more than 1024 rows; fc NULL or [B,N,N] f64.
+ * Equivalent to nrem_sweep_begin(homogeneous = -1) + nrem_sweep_advance(all) + nrem_sweep_finish: everything is enqueued on
+ * `stream` and the call returns without waiting for the kernels, except for ONE stream synchronisation inside begin (the
+ * homogeneity of the maps is read back to pick the kernel specialisation; pass the hint through nrem_sweep_begin to avoid it). */
 int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,
                    const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                    const int32_t* h_map_id, const uint64_t* streams, const double* emp,
                    double* gof, double* extra, double* fc, void* stream);
 
-/* Optional device-side timing of the next nrem_sweep_run calls (CUDA events on the caller's stream).
- * nrem_sweep_get_profile blocks until the last run has finished and fills h_out[4] (host) with
- * {whole pipeline ms, integrator ms of tile group 0, its launches, number of tile groups}.                      */
+/* The same run cut into pieces (the time loop is sequential, so a long sweep can be advanced slice by slice with the state kept
+ * in the plan; bench.py times such slices).  All three calls only enqueue work on `stream`.
+ *   begin   : stages the inputs and rewinds the plan to Euler step 0.  homogeneous: 1 = every entry of mapG/mapS is exactly 1
+ *             (scalar G and sigma per simulation: the specialised kernel), 0 = not, -1 = find out on the device (synchronises once).
+ *   advance : enqueues at most max_chunks integrator launches (one launch = chunk_samples * downsamp Euler steps of every
+ *             simulation, never crossing a phase boundary; a whole run has nrem_sweep_chunks_total of them) plus the
+ *             BOLD/filter launches that consume their samples; *h_chunks_left (host, may be NULL) = launches still to go.
+ *   finish  : backward filter pass, FC, GoF, sync/meta/peakfreq of a run whose integration is complete (outputs as nrem_sweep_run). */
+int nrem_sweep_begin(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,
+                     const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                     const int32_t* h_map_id, const uint64_t* streams, int homogeneous, void* stream);
+int64_t nrem_sweep_chunks_total(const nrem_sweep_plan* plan);
+int nrem_sweep_advance(nrem_sweep_plan* plan, int64_t max_chunks, int64_t* h_chunks_left, void* stream);
+int nrem_sweep_finish(nrem_sweep_plan* plan, const double* emp, double* gof, double* extra, double* fc, void* stream);
+
+/* Test hook for the deterministic stages of the sweep: instead of integrating, feed stored E samples (what run() records,
+ * netwWilsonCowanPlastic.py:129-130) to the plan's own BOLD / forward-filter / spectrum kernels, then call nrem_sweep_finish.
+ *   E [rows, N, Bpad] f32, simulation fastest, Bpad = B rounded up to NREM_TILE_SIMS; rows are consecutive stored samples
+ *   continuing where the previous call stopped (after nrem_sweep_begin: row 0); every call but the last must bring a
+ *   multiple of chunk_samples rows.                                                                                   */
+int nrem_sweep_feed_samples(nrem_sweep_plan* plan, const float* E, int64_t rows, void* stream);
+
+/* Optional device-side timing (CUDA events on the caller's stream and on tile group 0's stream).
+ * nrem_sweep_get_profile blocks until the enqueued work has finished, fills h_out[4] (host) with
+ * {device ms of the begin/advance/finish/run calls, integrator ms of tile group 0, its launches, number of tile groups}
+ * accumulated since the previous get_profile (or set_profiling) call, and starts a new accumulation.             */
 int nrem_sweep_set_profiling(nrem_sweep_plan* plan, int on);
 int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out);
 

@@ -284,6 +284,13 @@ int nrem_kuramoto_f64(const double* bold, int B, int64_t J, int N, double* sync_
 
 // ---- fused sweep -------------------------------------------------------------------------------
 
+// Position of a (possibly sliced) run inside the three phases: the next integrator launch starts at step i0 of phase ph.
+struct IntegCursor {
+    int ph;
+    int64_t i0, step;
+    int first;          // 1 until the first launch (which starts from E0, I0, a_ie_0 instead of the stored state)
+};
+
 struct nrem_sweep_plan {
     nrem_wc_params p;
     nrem_sweep_opts o;
@@ -300,7 +307,16 @@ struct nrem_sweep_plan {
     uint64_t* streams;
     void* bw_state;
     double *bold_dec, *fc;
-    double *obs, *hilb;            // [3][B] observables scratch, [J] Hilbert kernel
+    double *obs, *hilb;            // [3][B] observables scratch, [J] Hilbert kernel (filled at create)
+    int* dflag;                    // homogeneity flag (begin with homogeneous = -1)
+    // pinned host staging of the per-tile map ids, and the event after which it may be overwritten
+    int32_t* h_tm;
+    cudaEvent_t tm_done;
+    // state of the run in flight
+    IntegCursor cur;
+    int homo;
+    bool begun;
+    int64_t fed_rows;              // rows consumed through nrem_sweep_feed_samples
     // Welch spectrum (optional)
     WelchPlan welch;
     int64_t ring_rows;             // rows of the integrator's row-major E chunk buffer
@@ -308,16 +324,17 @@ struct nrem_sweep_plan {
     int welch_nseg;
     float* welchP;                 // [Bs][nperseg/2 + 1]
     int welch_smem;
-    // optional timing of the integrator launches (CUDA events on the caller's stream)
     // tile groups: more tiles than SMs are run as independent streams so that the hardware block
     // scheduler keeps every SM busy across chunk boundaries (see integrate())
     int last_groups;
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> gjoin;
     cudaEvent_t gfork;
+    // optional timing: (begin, end) event pairs around every API call on the caller's stream and around every
+    // integrator launch of tile group 0
     bool prof_on;
-    std::vector<cudaEvent_t> ev;      // [0] pipeline start, [1] pipeline end, then (begin, end) per integrator launch
-    int ev_used;
+    std::vector<cudaEvent_t> span_ev, ev;
+    int span_used, ev_used;
 };
 
 static BatchConst make_const(const nrem_wc_params& p) {
@@ -360,36 +377,55 @@ struct StagePtrs {
     uint64_t* streams;
 };
 
+__global__ void fill_strided_f64_kernel(double* dst, int64_t n, int64_t stride, int width, double v) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n * width) dst[(k / width) * stride + (k % width)] = v;
+}
+
 // Copies/convert the float64 API arrays into the padded float32 device layout.
+//   homo_hint: 1 / 0 = the caller states whether every map entry is exactly 1; -1 = decide on the device (one stream sync).
+//   h_tm     : pinned staging for the tile map (asynchronous copy); NULL = pageable vector + sync (blocking test hooks).
 static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, const double* CM, const double* mapG,
                         const double* mapS, const double* G0, const double* dG, const double* s0, const double* ds,
-                        const int32_t* h_map_id, const uint64_t* streams, const StagePtrs& d, cudaStream_t st, int* homo) {
+                        const int32_t* h_map_id, const uint64_t* streams, const StagePtrs& d, cudaStream_t st, int homo_hint,
+                        int* dflag, int32_t* h_tm, cudaEvent_t tm_done, int* homo) {
     const int N = p.nnodes;
-    std::vector<int32_t> tm((size_t)(Bs / kTile));
+    std::vector<int32_t> tm_local;
+    int32_t* tm = h_tm;
+    if (!tm) { tm_local.resize((size_t)(Bs / kTile)); tm = tm_local.data(); }
+    else if (tm_done) NREM_CUDA(cudaEventSynchronize(tm_done));       // previous run's copy has left the staging buffer
     for (int64_t t = 0; t < Bs / kTile; ++t) {
         const int64_t first = t * kTile;
         const int32_t m = h_map_id ? h_map_id[std::min<int64_t>(first, B - 1)] : 0;
         if (m < 0 || m >= n_maps) return fail(NREM_ERR_ARG, "map_id out of range%s%s");
         for (int64_t s = first; s < std::min<int64_t>(first + kTile, B); ++s)
             if (h_map_id && h_map_id[s] != m) return fail(NREM_ERR_ARG, "all simulations of a 128-tile must share map_id%s%s");
-        tm[(size_t)t] = m;
+        tm[t] = m;
     }
-    NREM_CUDA(cudaMemcpyAsync(d.tile_map, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice, st));
-    NREM_CUDA(cudaStreamSynchronize(st));
+    NREM_CUDA(cudaMemcpyAsync(d.tile_map, tm, (size_t)(Bs / kTile) * 4, cudaMemcpyHostToDevice, st));
+    if (h_tm) { if (tm_done) NREM_CUDA(cudaEventRecord(tm_done, st)); }
+    else NREM_CUDA(cudaStreamSynchronize(st));
     stage_sc_kernel<<<(kNPad * kNPad + 255) / 256, 256, 0, st>>>(CM, N, d.SCp);
     NREM_LAUNCHED();
     stage_maps_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(mapG, mapS, n_maps, N, d.mapG, d.mapS);
     NREM_LAUNCHED();
-    {   // homogeneous sweep (every map entry exactly 1)?  Decided once per sweep on the staged float32 maps.
-        int* dflag = nullptr;
-        int one = 1;
-        NREM_CUDA(cudaMalloc(&dflag, sizeof(int)));
-        NREM_CUDA(cudaMemcpyAsync(dflag, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-        maps_all_ones_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(d.mapG, d.mapS, n_maps, N, dflag);
-        NREM_LAUNCHED();
-        NREM_CUDA(cudaMemcpyAsync(homo, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        NREM_CUDA(cudaStreamSynchronize(st));
-        cudaFree(dflag);
+    if (homo_hint >= 0) {
+        *homo = homo_hint ? 1 : 0;
+    } else {   // homogeneous sweep (every map entry exactly 1)?  Decided once per sweep on the staged float32 maps.
+        int* flag = dflag;
+        if (!flag) NREM_CUDA(cudaMalloc(&flag, sizeof(int)));
+        cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+        if (e == cudaSuccess) {
+            maps_not_all_ones_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(d.mapG, d.mapS, n_maps, N, flag);
+            ++g_launches;
+            e = cudaGetLastError();
+        }
+        int not_homo = 1;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&not_homo, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (!dflag) cudaFree(flag);
+        if (e != cudaSuccess) return fail(NREM_ERR_CUDA, "homogeneity check: %s%s", cudaGetErrorString(e));
+        *homo = not_homo ? 0 : 1;
     }
     stage_par_kernel<<<(unsigned)((Bs + 255) / 256), 256, 0, st>>>(G0, dG, s0, ds, streams, B, Bs, d.par, d.streams);
     NREM_LAUNCHED();
@@ -405,7 +441,9 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     nrem_sweep_plan* P = new (std::nothrow) nrem_sweep_plan();
     if (!P) return fail(NREM_ERR_ARG, "out of host memory%s%s");
     P->p = *p; P->o = *o; P->B = B; P->n_maps = n_maps; P->K = K; P->N = p->nnodes; P->dev = nullptr;
-    P->prof_on = false; P->ev_used = 0; P->gfork = nullptr; P->last_groups = 1;
+    P->prof_on = false; P->ev_used = 0; P->span_used = 0; P->gfork = nullptr; P->last_groups = 1;
+    P->h_tm = nullptr; P->tm_done = nullptr; P->begun = false; P->fed_rows = 0; P->homo = 0;
+    P->cur = IntegCursor{0, 0, 0, 1};
     P->Bs = round_up(B, kTile); P->tiles = P->Bs / kTile;
     P->T = (p->n3 + p->downsamp - 1) / p->downsamp;
     P->Tf = P->T - o->Neq;
@@ -452,6 +490,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int64_t o_fc = take(8 * (int64_t)B * N * N);
     const int64_t o_obs = take(8 * 3 * (int64_t)B);
     const int64_t o_hil = take(8 * std::max<int64_t>(P->J, 1));
+    const int64_t o_flag = take(16);
     const int WL = P->welch.L, WM = WL / 2;
     const int64_t o_wr = take(4 * (int64_t)WL * P->nth);
     const int64_t o_wp = take(WL ? 4 * P->Bs * (int64_t)(WM + 1) : 0), o_ww = take(4 * (int64_t)WL), o_wt = take(8 * (int64_t)WM), o_wt2 = take(8 * (int64_t)(WM + 1));
@@ -466,7 +505,11 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->S = carve_filt((double*)(base + o_fs), P->nth, P->J, o->bold_downsamp, &ptab_dev);
     P->fh.f.ptab = ptab_dev;
     P->bold_dec = (double*)(base + o_bd); P->fc = (double*)(base + o_fc);
-    P->obs = (double*)(base + o_obs); P->hilb = (double*)(base + o_hil);
+    P->obs = (double*)(base + o_obs); P->hilb = (double*)(base + o_hil); P->dflag = (int*)(base + o_flag);
+    auto bail = [&](const char* what, cudaError_t err) {
+        nrem_sweep_destroy(P);
+        return fail(NREM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    };
     if (WL) {
         P->welchP = (float*)(base + o_wp);
         P->wring = (float*)(base + o_wr);
@@ -475,10 +518,18 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
         if (ew == cudaSuccess) ew = cudaMemcpy(base + o_wt, h_tw.data(), 8 * (size_t)WM, cudaMemcpyHostToDevice);
         if (ew == cudaSuccess) ew = cudaMemcpy(base + o_wt2, h_tw2.data(), 8 * (size_t)(WM + 1), cudaMemcpyHostToDevice);
         if (ew == cudaSuccess) ew = cudaFuncSetAttribute(welch_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P->welch_smem);
-        if (ew != cudaSuccess) { cudaFree(P->dev); delete P; return fail(NREM_ERR_CUDA, "welch setup: %s%s", cudaGetErrorString(ew)); }
+        if (ew != cudaSuccess) return bail("welch setup", ew);
     }
     e = cudaMemcpy(ptab_dev, P->fh.ptab.data(), P->fh.ptab.size() * 8, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(P->dev); delete P; return fail(NREM_ERR_CUDA, "cudaMemcpy(ptab): %s%s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return bail("cudaMemcpy(ptab)", e);
+    if (P->J <= 1024) {                     // Hilbert kernel of the Kuramoto observables: built once, here
+        const std::vector<double> g = hilbert_kernel(P->J);
+        e = cudaMemcpy(P->hilb, g.data(), sizeof(double) * (size_t)P->J, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return bail("cudaMemcpy(hilbert kernel)", e);
+    }
+    e = cudaMallocHost((void**)&P->h_tm, sizeof(int32_t) * (size_t)P->tiles);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->tm_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) return bail("pinned staging", e);
     *plan = P;
     return NREM_OK;
 }
@@ -486,7 +537,10 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
 int nrem_sweep_destroy(nrem_sweep_plan* plan) {
     if (!plan) return NREM_OK;
     if (plan->dev) cudaFree(plan->dev);
+    if (plan->h_tm) cudaFreeHost(plan->h_tm);
+    if (plan->tm_done) cudaEventDestroy(plan->tm_done);
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->span_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : plan->gjoin) cudaEventDestroy(e);
     for (cudaStream_t g : plan->gstreams) cudaStreamDestroy(g);
     if (plan->gfork) cudaEventDestroy(plan->gfork);
@@ -496,8 +550,41 @@ int nrem_sweep_destroy(nrem_sweep_plan* plan) {
 
 int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan) { return plan ? plan->dev_bytes : -1; }
 
-// Runs phases 1-3; when Ebuf_all != NULL every sample goes to it (test hook), otherwise the
-// samples of each chunk are consumed by the BOLD/filter kernel of the plan.
+static int64_t chunks_total(const nrem_wc_params& p, int chunk_samples) {
+    const int64_t cs = (int64_t)chunk_samples * p.downsamp;
+    return (p.n1 + cs - 1) / cs + (p.n2 + cs - 1) / cs + (p.n3 + cs - 1) / cs;
+}
+
+int64_t nrem_sweep_chunks_total(const nrem_sweep_plan* plan) { return plan ? chunks_total(plan->p, plan->chunk_samples) : -1; }
+
+// BOLD / forward filter (+ optional spectrum) over `rows` stored samples starting at stored row `row_base`, for the
+// simulations [sim0, sim0 + nsim); Echunk points at the first of these rows, layout [rows][N][Bs].
+static int launch_bold_chunk(nrem_sweep_plan* plan, const float* Echunk, int rows, int64_t row_base, int64_t sim0, int64_t nsim,
+                             cudaStream_t st) {
+    const unsigned blocks = (unsigned)((plan->N * nsim + 127) / 128);
+    const int64_t Bs = plan->Bs;
+    if (plan->o.bold_f32)
+        bold_filter_chunk_kernel<float><<<blocks, 128, 0, st>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
+                                                               (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
+    else
+        bold_filter_chunk_kernel<double><<<blocks, 128, 0, st>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
+                                                                plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
+    NREM_LAUNCHED();
+    // Welch: a segment [e - L, e) is complete whenever e >= L and (e - L) is a multiple of the hop L/2
+    const int64_t e_row = row_base + rows;
+    if (plan->welch.L > 0 && e_row >= plan->welch.L && (e_row - plan->welch.L) % plan->welch.M == 0) {
+        const double wsum2 = 0.375 * plan->welch.L;             // sum of a periodic Hann window squared
+        const float scale = (float)(1.0 / (plan->o.welch_fs * wsum2) / plan->welch_nseg / plan->N);
+        welch_segment_kernel<<<(unsigned)((nsim + kWelchSims - 1) / kWelchSims), kWelchThreads, plan->welch_smem, st>>>(
+            plan->wring, (int)((e_row - plan->welch.L) % plan->welch.L), plan->N, Bs, sim0, nsim, plan->welch, plan->welchP, scale);
+        NREM_LAUNCHED();
+    }
+    return NREM_OK;
+}
+
+// Runs (part of) phases 1-3 from the cursor position: at most max_chunks integrator launches per tile group.  When
+// Ebuf_all != NULL every sample goes to it (test hook), otherwise the samples of each chunk are consumed by the
+// BOLD/filter kernel of the plan.
 //
 // Scheduling: a tile (128 simulations) occupies one SM for a whole launch.  With more tiles than SMs a
 // single grid would need two waves per launch, the second almost empty; instead the tiles are split into
@@ -505,7 +592,7 @@ int64_t nrem_sweep_device_bytes(const nrem_sweep_plan* plan) { return plan ? pla
 // Chains are independent, so whenever one group's CTAs retire, waiting CTAs of any other group take the
 // SMs: the sweep costs tiles/SMs "rounds" instead of ceil(tiles/SMs).
 static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, int64_t Bs, int chunk_samples,
-                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st, int homo) {
+                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st, int homo, IntegCursor& cur, int64_t max_chunks) {
     BatchArgs A;
     A.c = make_const(p);
     A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
@@ -532,62 +619,45 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
     }
     const int64_t ns[3] = {p.n1, p.n2, p.n3};
     const int64_t chunk_steps = (int64_t)chunk_samples * p.downsamp;
-    int64_t step = 0;
-    bool first = true;
-    for (int ph = 0; ph < 3; ++ph) {
+    for (int64_t done = 0; cur.ph < 3 && done < max_chunks;) {
+        const int ph = cur.ph;
+        const int64_t i0 = cur.i0;
+        if (i0 >= ns[ph]) { ++cur.ph; cur.i0 = 0; continue; }
         A.kA = (float)(p.dtSim / p.tau_ip[ph]);
-        for (int64_t i0 = 0; i0 < ns[ph]; i0 += chunk_steps) {
-            const int64_t n = std::min(chunk_steps, ns[ph] - i0);
-            A.step0 = (uint32_t)step; A.nsteps = (int)n; A.init = first ? 1 : 0;
-            A.rec = (ph == 2); A.rec_phase = 0;        // chunks start on a multiple of downsamp
-            const int64_t row_base = i0 / p.downsamp;
-            const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
-            const int64_t ring = plan ? plan->ring_rows : chunk_samples;
-            const int64_t ring_row0 = row_base % ring;
-            if (Ebuf_all) { A.Ebuf = Ebuf_all; A.row0 = row_base; }
-            else { A.Ebuf = d.Ebuf; A.row0 = ring_row0; }
-            for (int g = 0; g < ngroups; ++g) {
-                const int64_t t0 = tiles * g / ngroups, t1 = tiles * (g + 1) / ngroups;
-                A.tile0 = (int)t0;
-                cudaEvent_t e0 = nullptr, e1 = nullptr;
-                if (plan && plan->prof_on && g == 0) {
-                    while ((int)plan->ev.size() < plan->ev_used + 2) {
-                        cudaEvent_t e;
-                        NREM_CUDA(cudaEventCreate(&e));
-                        plan->ev.push_back(e);
-                    }
-                    e0 = plan->ev[plan->ev_used]; e1 = plan->ev[plan->ev_used + 1];
-                    plan->ev_used += 2;
-                    NREM_CUDA(cudaEventRecord(e0, gs[g]));
+        const int64_t n = std::min(chunk_steps, ns[ph] - i0);
+        A.step0 = (uint32_t)cur.step; A.nsteps = (int)n; A.init = cur.first ? 1 : 0;
+        A.rec = (ph == 2); A.rec_phase = 0;        // chunks start on a multiple of downsamp
+        const int64_t row_base = i0 / p.downsamp;
+        const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
+        const int64_t ring = plan ? plan->ring_rows : chunk_samples;
+        const int64_t ring_row0 = row_base % ring;
+        if (Ebuf_all) { A.Ebuf = Ebuf_all; A.row0 = row_base; }
+        else { A.Ebuf = d.Ebuf; A.row0 = ring_row0; }
+        for (int g = 0; g < ngroups; ++g) {
+            const int64_t t0 = tiles * g / ngroups, t1 = tiles * (g + 1) / ngroups;
+            A.tile0 = (int)t0;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (plan && plan->prof_on && g == 0) {
+                while ((int)plan->ev.size() < plan->ev_used + 2) {
+                    cudaEvent_t e;
+                    NREM_CUDA(cudaEventCreate(&e));
+                    plan->ev.push_back(e);
                 }
-                if (int rc = launch_integrator(kernel, A, t1 - t0, gs[g])) return rc;
-                if (e1) NREM_CUDA(cudaEventRecord(e1, gs[g]));
-                if (ph == 2 && plan) {
-                    const int64_t sim0 = t0 * kTile, nsim = (t1 - t0) * kTile;
-                    const unsigned blocks = (unsigned)((plan->N * nsim + 127) / 128);
-                    const float* Echunk = d.Ebuf + ring_row0 * (int64_t)plan->N * Bs;
-                    if (plan->o.bold_f32)
-                        bold_filter_chunk_kernel<float><<<blocks, 128, 0, gs[g]>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
-                                                                                (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
-                    else
-                        bold_filter_chunk_kernel<double><<<blocks, 128, 0, gs[g]>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
-                                                                                 plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
-                    NREM_LAUNCHED();
-                    // Welch: a segment [e - L, e) is complete whenever e >= L and (e - L) is a multiple of the hop L/2
-                    const int64_t e_row = row_base + rows;
-                    if (plan->welch.L > 0 && e_row >= plan->welch.L && (e_row - plan->welch.L) % plan->welch.M == 0) {
-                        const double wsum2 = 0.375 * plan->welch.L;             // sum of a periodic Hann window squared
-                        const float scale = (float)(1.0 / (plan->o.welch_fs * wsum2) / plan->welch_nseg / plan->N);
-                        welch_segment_kernel<<<(unsigned)((nsim + kWelchSims - 1) / kWelchSims), kWelchThreads, plan->welch_smem, gs[g]>>>(
-                            plan->wring, (int)((e_row - plan->welch.L) % plan->welch.L), plan->N, Bs, sim0, nsim, plan->welch, plan->welchP, scale);
-                        NREM_LAUNCHED();
-                    }
-                }
+                e0 = plan->ev[plan->ev_used]; e1 = plan->ev[plan->ev_used + 1];
+                plan->ev_used += 2;
+                NREM_CUDA(cudaEventRecord(e0, gs[g]));
             }
-            step += n;
-            first = false;
+            if (int rc = launch_integrator(kernel, A, t1 - t0, gs[g])) return rc;
+            if (e1) NREM_CUDA(cudaEventRecord(e1, gs[g]));
+            if (ph == 2 && plan) {
+                const float* Echunk = d.Ebuf + ring_row0 * (int64_t)plan->N * Bs;
+                if (int rc = launch_bold_chunk(plan, Echunk, rows, row_base, t0 * kTile, (t1 - t0) * kTile, gs[g])) return rc;
+            }
         }
+        cur.i0 += n; cur.step += n; cur.first = 0;
+        ++done;
     }
+    while (cur.ph < 3 && cur.i0 >= ns[cur.ph]) { ++cur.ph; cur.i0 = 0; }
     if (ngroups > 1) {
         for (int g = 0; g < ngroups; ++g) {
             NREM_CUDA(cudaEventRecord(plan->gjoin[g], gs[g]));
@@ -597,23 +667,87 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
     return NREM_OK;
 }
 
-int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, const double* mapS,
-                   const double* G0, const double* dG, const double* sigma0, const double* dsigma,
-                   const int32_t* h_map_id, const uint64_t* streams, const double* emp,
-                   double* gof, double* extra, double* fc, void* stream) {
-    NREM_REQUIRE(P, "plan is null");
-    NREM_REQUIRE(CM && mapG && mapS && G0 && dG && sigma0 && dsigma && streams && emp && gof, "null array");
-    cudaStream_t st = (cudaStream_t)stream;
-    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
-    if (P->prof_on) {
-        while (P->ev.size() < 2) { cudaEvent_t e; NREM_CUDA(cudaEventCreate(&e)); P->ev.push_back(e); }
-        P->ev_used = 2;
-        NREM_CUDA(cudaEventRecord(P->ev[0], st));
+// (begin, end) events around one API call on the caller's stream, when profiling is on
+struct SpanTimer {
+    nrem_sweep_plan* P;
+    cudaStream_t st;
+    cudaEvent_t end;
+    SpanTimer(nrem_sweep_plan* plan, cudaStream_t s) : P(plan), st(s), end(nullptr) {
+        if (!P->prof_on) return;
+        while ((int)P->span_ev.size() < P->span_used + 2) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            P->span_ev.push_back(e);
+        }
+        cudaEventRecord(P->span_ev[P->span_used], st);
+        end = P->span_ev[P->span_used + 1];
+        P->span_used += 2;
     }
+    ~SpanTimer() { if (end) cudaEventRecord(end, st); }
+};
+
+int nrem_sweep_begin(nrem_sweep_plan* P, const double* CM, const double* mapG, const double* mapS,
+                     const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                     const int32_t* h_map_id, const uint64_t* streams, int homogeneous, void* stream) {
+    NREM_REQUIRE(P, "plan is null");
+    NREM_REQUIRE(CM && mapG && mapS && G0 && dG && sigma0 && dsigma && streams, "null array");
+    NREM_REQUIRE(homogeneous >= -1 && homogeneous <= 1, "homogeneous must be -1, 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpanTimer span(P, st);
+    P->begun = false;
+    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
     if (P->welchP) NREM_CUDA(cudaMemsetAsync(P->welchP, 0, 4 * P->Bs * (size_t)(P->welch.M + 1), st));
-    int homo = 0;
-    if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, &homo)) return rc;
-    if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st, homo)) return rc;
+    if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st,
+                              homogeneous, P->dflag, P->h_tm, P->tm_done, &P->homo)) return rc;
+    P->cur = IntegCursor{0, 0, 0, 1};
+    P->fed_rows = 0;
+    P->begun = true;
+    return NREM_OK;
+}
+
+int nrem_sweep_advance(nrem_sweep_plan* P, int64_t max_chunks, int64_t* h_chunks_left, void* stream) {
+    NREM_REQUIRE(P, "plan is null");
+    NREM_REQUIRE(P->begun, "nrem_sweep_begin has not been called");
+    NREM_REQUIRE(max_chunks >= 0, "max_chunks must be non-negative");
+    NREM_REQUIRE(P->fed_rows == 0, "this run is being fed with stored samples");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpanTimer span(P, st);
+    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
+    if (max_chunks > 0)
+        if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st, P->homo, P->cur, max_chunks)) return rc;
+    if (h_chunks_left) {
+        const int64_t cs = (int64_t)P->chunk_samples * P->p.downsamp;
+        const int64_t ns[3] = {P->p.n1, P->p.n2, P->p.n3};
+        int64_t left = 0;
+        for (int ph = P->cur.ph; ph < 3; ++ph) left += (ns[ph] - (ph == P->cur.ph ? P->cur.i0 : 0) + cs - 1) / cs;
+        *h_chunks_left = left;
+    }
+    return NREM_OK;
+}
+
+int nrem_sweep_feed_samples(nrem_sweep_plan* P, const float* E, int64_t rows, void* stream) {
+    NREM_REQUIRE(P && E, "null argument");
+    NREM_REQUIRE(P->begun, "nrem_sweep_begin has not been called");
+    NREM_REQUIRE(P->cur.step == 0, "this run is being integrated");
+    NREM_REQUIRE(rows >= 1 && P->fed_rows + rows <= P->T, "more rows than the plan's recording phase holds");
+    NREM_REQUIRE(P->fed_rows % P->chunk_samples == 0, "a previous call did not bring a multiple of chunk_samples rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpanTimer span(P, st);
+    for (int64_t r = 0; r < rows; r += P->chunk_samples) {
+        const int n = (int)std::min<int64_t>(P->chunk_samples, rows - r);
+        if (int rc = launch_bold_chunk(P, E + r * (int64_t)P->N * P->Bs, n, P->fed_rows + r, 0, P->Bs, st)) return rc;
+    }
+    P->fed_rows += rows;
+    return NREM_OK;
+}
+
+int nrem_sweep_finish(nrem_sweep_plan* P, const double* emp, double* gof, double* extra, double* fc, void* stream) {
+    NREM_REQUIRE(P, "plan is null");
+    NREM_REQUIRE(emp && gof, "null array");
+    NREM_REQUIRE(P->begun, "nrem_sweep_begin has not been called");
+    NREM_REQUIRE(P->cur.ph >= 3 || P->fed_rows == P->T, "the integration of this run is not complete");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpanTimer span(P, st);
     const int N = P->N;
     filt_backward_kernel<<<(unsigned)((P->nth + 127) / 128), 128, 0, st>>>(P->fh.f, P->S, P->nth, N, P->Bs, 1, P->bold_dec,
                                                                          P->J * N, N, 1, P->B);
@@ -622,21 +756,24 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
     if (int rc = nrem_fc_f64(P->bold_dec, P->B, P->J, N, fcd, stream)) return rc;
     double* meanfc = nullptr;
     if (extra) {
-        NREM_CUDA(cudaMemsetAsync(extra, 0, sizeof(double) * 4 * P->B, st));
+        const double nan_v = __builtin_nan("");
+        const unsigned fb = (unsigned)((2 * (int64_t)P->B + 255) / 256);
         // sync / meta (utils.kuramoto on the decimated BOLD, whole_sweep_both.py:93) -> plan scratch [B][2]
         if (P->J <= 1024) {
-            if (int rc = nrem_kuramoto_f64(P->bold_dec, P->B, P->J, N, P->obs, P->hilb, stream)) return rc;
+            kuramoto_f64_kernel<<<P->B, (int)round_up(P->J, 32), sizeof(double) * (P->J + 40), st>>>(P->bold_dec, P->hilb, (int)P->J, N, P->obs);
+            NREM_LAUNCHED();
             NREM_CUDA(cudaMemcpy2DAsync(extra + 1, 4 * sizeof(double), P->obs, 2 * sizeof(double), 2 * sizeof(double), P->B,
                                         cudaMemcpyDeviceToDevice, st));
+        } else {
+            fill_strided_f64_kernel<<<fb, 256, 0, st>>>(extra + 1, P->B, 4, 2, nan_v);       // not computed: never a plausible 0.0
+            NREM_LAUNCHED();
         }
         if (P->welchP) {
             welch_peak_kernel<<<P->B, 256, 0, st>>>(P->welchP, P->welch.M + 1, P->o.welch_fs / P->welch.L, extra + 3, 4);
             NREM_LAUNCHED();
         } else {
-            const double nan_v = __builtin_nan("");
-            std::vector<double> nanv((size_t)P->B, nan_v);
-            NREM_CUDA(cudaMemcpy2DAsync(extra + 3, 4 * sizeof(double), nanv.data(), sizeof(double), sizeof(double), P->B, cudaMemcpyHostToDevice, st));
-            NREM_CUDA(cudaStreamSynchronize(st));
+            fill_strided_f64_kernel<<<fb, 256, 0, st>>>(extra + 3, P->B, 4, 1, nan_v);
+            NREM_LAUNCHED();
         }
         meanfc = P->obs + 2 * (int64_t)P->B;         // mean FC -> extra[b][0]
     }
@@ -645,32 +782,48 @@ int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, con
         NREM_CUDA(cudaMemcpy2DAsync(extra, 4 * sizeof(double), meanfc, sizeof(double), sizeof(double), P->B,
                                     cudaMemcpyDeviceToDevice, st));
     }
-    if (P->prof_on) NREM_CUDA(cudaEventRecord(P->ev[1], st));
     return NREM_OK;
+}
+
+int nrem_sweep_run(nrem_sweep_plan* P, const double* CM, const double* mapG, const double* mapS,
+                   const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                   const int32_t* h_map_id, const uint64_t* streams, const double* emp,
+                   double* gof, double* extra, double* fc, void* stream) {
+    NREM_REQUIRE(P, "plan is null");
+    NREM_REQUIRE(emp && gof, "null array");
+    if (int rc = nrem_sweep_begin(P, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, -1, stream)) return rc;
+    if (int rc = nrem_sweep_advance(P, chunks_total(P->p, P->chunk_samples), nullptr, stream)) return rc;
+    return nrem_sweep_finish(P, emp, gof, extra, fc, stream);
 }
 
 int nrem_sweep_set_profiling(nrem_sweep_plan* plan, int on) {
     NREM_REQUIRE(plan, "plan is null");
     plan->prof_on = on != 0;
     plan->ev_used = 0;
+    plan->span_used = 0;
     return NREM_OK;
 }
 
 int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out) {
     NREM_REQUIRE(plan && h_out, "null argument");
-    NREM_REQUIRE(plan->prof_on && plan->ev_used >= 2, "profiling was not enabled for the last run");
-    NREM_CUDA(cudaEventSynchronize(plan->ev[1]));
+    NREM_REQUIRE(plan->prof_on && plan->span_used >= 2, "profiling was not enabled, or nothing ran since the last call");
+    NREM_CUDA(cudaEventSynchronize(plan->span_ev[plan->span_used - 1]));
     float ms = 0.f;
-    NREM_CUDA(cudaEventElapsedTime(&ms, plan->ev[0], plan->ev[1]));
-    h_out[0] = ms;
-    double k1 = 0.0;
-    for (int i = 2; i + 1 < plan->ev_used; i += 2) {
+    double total = 0.0, k1 = 0.0;
+    for (int i = 0; i + 1 < plan->span_used; i += 2) {
+        NREM_CUDA(cudaEventElapsedTime(&ms, plan->span_ev[i], plan->span_ev[i + 1]));
+        total += ms;
+    }
+    for (int i = 0; i + 1 < plan->ev_used; i += 2) {
         NREM_CUDA(cudaEventElapsedTime(&ms, plan->ev[i], plan->ev[i + 1]));
         k1 += ms;
     }
+    h_out[0] = total;
     h_out[1] = k1;
-    h_out[2] = (plan->ev_used - 2) / 2;
+    h_out[2] = plan->ev_used / 2;
     h_out[3] = (double)plan->last_groups;
+    plan->ev_used = 0;
+    plan->span_used = 0;
     return NREM_OK;
 }
 
@@ -701,13 +854,15 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     StagePtrs d{(float*)(base + o_st4), (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
                 (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
     int homo = 0;
-    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, &homo);
+    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, -1, nullptr, nullptr, nullptr, &homo);
+    IntegCursor cur{0, 0, 0, 1};
+    const int64_t all = (int64_t)1 << 60;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     if (rc == NREM_OK) {
         cudaEventRecord(t0, st);
-        if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st, homo);
-        else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st, homo);   // samples go to a scratch ring
+        if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st, homo, cur, all);
+        else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st, homo, cur, all);   // samples go to a scratch ring
         cudaEventRecord(t1, st);
         if (rc == NREM_OK) {
             const int64_t n = (int64_t)N * Bs;

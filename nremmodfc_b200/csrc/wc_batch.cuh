@@ -198,11 +198,11 @@ __global__ void stage_maps_kernel(const double* mapG, const double* mapS, int n_
     oG[k] = i < N ? (float)mapG[(size_t)m * N + i] : 0.f;
     oS[k] = i < N ? (float)mapS[(size_t)m * N + i] : 0.f;
 }
-// flag[0] &= (every real map entry == 1)
-__global__ void maps_all_ones_kernel(const float* mG, const float* mS, int n_maps, int N, int* flag) {
+// flag[0] (zeroed by the caller) becomes 1 when some real map entry differs from 1
+__global__ void maps_not_all_ones_kernel(const float* mG, const float* mS, int n_maps, int N, int* flag) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_maps * kNPad) return;
-    if ((k % kNPad) < N && (mG[k] != 1.0f || mS[k] != 1.0f)) flag[0] = 0;
+    if ((k % kNPad) < N && (mG[k] != 1.0f || mS[k] != 1.0f)) flag[0] = 1;
 }
 __global__ void stage_par_kernel(const double* G0, const double* dG, const double* s0, const double* ds,
                                  const uint64_t* streams, int B, int64_t Bs, float* par, uint64_t* st) {

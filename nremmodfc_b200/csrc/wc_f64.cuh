@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(CM_SMEM ? 256 : 1024) wc_run_f64_kernel(const 
     auto npar = [&](int k, double scalar) { return (A.node_par && live) ? A.node_par[(size_t)k * N + i] : scalar; };
     const double a_ee = npar(0, p.a_ee), a_ei = npar(1, p.a_ei), a_ii = npar(2, p.a_ii), tauE = npar(3, p.tauE), tauI = npar(4, p.tauI);
     const double Pn = npar(5, p.P), rhoE = npar(6, p.rhoE), rE = npar(7, p.rE), rI = npar(8, p.rI), mu = npar(9, p.mu), sigmaI = npar(10, p.sigmaI);
+    a = npar(11, p.a_ie_0);                                   // a_ie = a_ie_0*np.ones(N) (netwWilsonCowanPlastic.py:93) broadcasts a vector
     const double G = live ? A.G[(size_t)b * N + i] : 0.0;
     const double sg = live ? A.sg[(size_t)b * N + i] : 1.0;
     const uint64_t strm = A.streams ? A.streams[b] : (uint64_t)b;

@@ -8,9 +8,11 @@ every call goes to the CUDA library; there is no numba and no CPU path.
 Differences (all supersets of the reference behaviour):
   * attributes are read at CALL time; ``recompile()`` is a no-op kept for compatibility
     (numba froze globals at JIT time and the drivers paid ~3 s of LLVM per simulation);
-  * ``sid`` really seeds the noise: the stream is counter-based Philox keyed by (sid, replicate),
-    so two calls with the same ``sid`` give the same trajectory.  (The reference's ``sid`` never
-    reached numba's generator.)  Set ``noise`` to an array [steps, N] to inject a stream instead;
+  * the noise stream is counter-based Philox keyed by (``sid``, replicate).  By default (``replicate = None``) the replicate id
+    is the number of ``run()`` calls made so far in this process, so consecutive calls draw fresh, independent noise exactly
+    as the reference does (its numba generator is never re-seeded: ``sid`` is a replicate label there) —
+    the 400 (dG, dsigma) cells a driver runs for one ``sid`` are statistically independent.  Set ``replicate`` to an integer to
+    pin the stream (same ``sid`` + ``replicate`` -> same trajectory), or ``noise`` to an array [steps, N] to inject one;
   * ``run()`` takes a length-N vector for any node parameter (reference line 21); the batched sweep (``sweep.SweepPlan``)
     takes per-node ``G`` and ``sigmaE``, the only ones the drivers vary per node.
 """
@@ -55,7 +57,8 @@ D = 0.002
 sqdtD = D / np.sqrt(dtSim)
 sid = 12
 noise = None            # extension: inject [len(timeTrans1)+len(timeTrans2)+len(timeSim), N] values (already scaled)
-replicate = 0           # extension: Philox stream id of this run
+replicate = None        # extension: Philox stream id of the next run; None = number of run() calls so far (fresh noise per call)
+_calls = 0
 
 # network parameters (reference lines 61-68)
 G = 0.7
@@ -85,7 +88,7 @@ def _node_vectors(nn):
 def _params(n1, n2, n3, nn):
     g = globals()
     sc = {name: float(np.mean(g[name])) for name in ops.NODE_PARAMS}        # vectors travel separately (_node_vectors)
-    return ops.make_params(nn, n1, n2, n3, a_ie_0=g["a_ie_0"], dtSim=g["dtSim"], sqdtD=g["sqdtD"],
+    return ops.make_params(nn, n1, n2, n3, dtSim=g["dtSim"], sqdtD=g["sqdtD"],
                            downsamp=int(g["dt"] / g["dtSim"]), seed=int(g["sid"]), **sc)
 
 
@@ -102,7 +105,9 @@ class _Run(_Recompilable):
         cm = np.asarray(g["CM"], dtype=np.float64)
         nn = len(cm)
         p = _params(len(g["timeTrans1"]), len(g["timeTrans2"]), len(g["timeSim"]), nn)
-        Y, _ = ops.wc_run(p, cm, g["G"], g["sigmaE"], B=1, streams=[int(g["replicate"])], noise=g["noise"],
+        rep = g["_calls"] if g["replicate"] is None else int(g["replicate"])
+        g["_calls"] += 1
+        Y, _ = ops.wc_run(p, cm, g["G"], g["sigmaE"], B=1, streams=[rep], noise=g["noise"],
                           nrec=len(g["time"]), want_Y=True, node_params=_node_vectors(nn) or None)
         return Y[0]
 
@@ -113,6 +118,9 @@ class _WilsonCowan(_Recompilable):
         g = globals()
         cm = np.asarray(g["CM"], dtype=np.float64)
         nn = len(cm)
+        vec = _node_vectors(nn)
+        if vec or np.ndim(mu) != 0:
+            raise ValueError("wilsonCowan(): per-node vectors for " + ", ".join(sorted(vec) or ["mu"]) + " are only supported by run()")
         p = _params(0, 0, 0, nn)
         p.mu = float(mu)
         nz = np.random.normal(0, g["sqdtD"], size=nn)

@@ -88,7 +88,7 @@ def _per_node(x, B, N, name):
     return np.ascontiguousarray(a)
 
 
-NODE_PARAMS = ("a_ee", "a_ei", "a_ii", "tauE", "tauI", "P", "rhoE", "rE", "rI", "mu", "sigmaI")     # NREM_NODE_PARAMS order
+NODE_PARAMS = ("a_ee", "a_ei", "a_ii", "tauE", "tauI", "P", "rhoE", "rE", "rI", "mu", "sigmaI", "a_ie_0")     # NREM_NODE_PARAMS order
 
 
 def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=True, node_params=None, device=None):
@@ -131,7 +131,7 @@ def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=Tr
         d_CM, d_G, d_sg = (to_device(x, torch.float64, dev) for x in (CM, G, sg))
         d_np = None if npar is None else to_device(npar, torch.float64, dev)
         d_st = _u64(np.arange(B) if streams is None else streams, dev)
-        d_Y = torch.empty((B, max(nrec, 1), 3, N), dtype=torch.float64, device=dev) if want_Y and nrec > 0 else None
+        d_Y = torch.zeros((B, max(nrec, 1), 3, N), dtype=torch.float64, device=dev) if want_Y and nrec > 0 else None   # rows beyond ceil(n3/downsamp) stay 0 (np.zeros, netwWilsonCowanPlastic.py:122)
         d_fin = torch.empty((B, 3, N), dtype=torch.float64, device=dev)
         check(lib.nrem_wc_run_f64_ex(C.byref(p), _ptr(d_CM), _ptr(d_G), _ptr(d_sg), _ptr(d_np), _ptr(d_st), _ptr(d_noise), nb, B,
                                      nrec, _ptr(d_Y), _ptr(d_fin), _stream()))
@@ -264,12 +264,19 @@ def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=No
     Bs = (B + 127) // 128 * 128
     nrec = (p.n3 + p.downsamp - 1) // p.downsamp
     mid = None if map_id is None else np.ascontiguousarray(map_id, dtype=np.int32)
+    if mapG.shape[1] != N or mapS.shape != mapG.shape:
+        raise ValueError(f"maps must be [n_maps, {N}]")
+    if mid is not None and (mid.shape != (B,) or mid.min() < 0 or mid.max() >= mapG.shape[0]):
+        raise ValueError(f"map_id must have shape ({B},) with values in [0, {mapG.shape[0]})")
+    streams = np.arange(B, dtype=np.uint64) if streams is None else np.asarray(streams, dtype=np.uint64)
+    if streams.shape != (B,):
+        raise ValueError(f"streams must have shape ({B},), got {streams.shape}")
     with torch.cuda.device(dev):
         d = [to_device(np.broadcast_to(np.asarray(a, dtype=np.float64), (B,)).copy(), torch.float64, dev)
              for a in (G0, dG, sigma0, dsigma)]
         d_CM = to_device(np.asarray(CM, dtype=np.float64), torch.float64, dev)
         d_mG, d_mS = to_device(mapG, torch.float64, dev), to_device(mapS, torch.float64, dev)
-        d_st = _u64(np.arange(B) if streams is None else streams, dev)
+        d_st = _u64(streams, dev)
         d_E = torch.empty((max(nrec, 1), N, Bs), dtype=torch.float32, device=dev) if record and nrec > 0 else None
         d_fin = torch.empty((3, N, Bs), dtype=torch.float32, device=dev)
         check(lib.nrem_sweep_integrate_f32(C.byref(p), KERNELS[kernel], _ptr(d_CM), _ptr(d_mG), _ptr(d_mS), _ptr(d[0]),

@@ -130,13 +130,15 @@ class SweepPlan:
             check(lib.nrem_sweep_create(C.byref(p), C.byref(o), self.B, self.n_maps, self.K, C.byref(self._plan)))
         self.device_bytes = int(lib.nrem_sweep_device_bytes(self._plan))
         T = (p.n3 + p.downsamp - 1) // p.downsamp
-        self.J = (T - int(Neq) + int(bold_downsamp) - 1) // int(bold_downsamp)
+        self.T, self.J = T, (T - int(Neq) + int(bold_downsamp) - 1) // int(bold_downsamp)
+        self._held = None
 
     def set_profiling(self, on=True):
         check(lib.nrem_sweep_set_profiling(self._plan, 1 if on else 0))
 
     def profile(self):
-        """Device times of the last run (blocks until it finished): dict(total_ms, integrator_ms, integrator_launches)."""
+        """Device times since the previous call (blocks until the enqueued work has finished):
+        dict(total_ms, integrator_ms, integrator_launches, tile_groups)."""
         out = (C.c_double * 4)()
         check(lib.nrem_sweep_get_profile(self._plan, out))
         return {"total_ms": out[0], "integrator_ms": out[1], "integrator_launches": int(out[2]), "tile_groups": int(out[3])}
@@ -145,6 +147,7 @@ class SweepPlan:
         if self._plan:
             lib.nrem_sweep_destroy(self._plan)
             self._plan = C.c_void_p()
+        self._held = None
 
     def __del__(self):
         try:
@@ -152,44 +155,120 @@ class SweepPlan:
         except Exception:
             pass
 
-    # -- device-resident call (bench `value`): tensors already in HBM ---------------------------
-    def run_device(self, d_CM, d_mapG, d_mapS, d_G0, d_dG, d_s0, d_ds, map_id, d_streams, d_emp, d_gof, d_extra, d_fc=None):
-        mid = None if map_id is None else np.ascontiguousarray(map_id, dtype=np.int32)
-        with torch.cuda.device(self.dev):
-            check(lib.nrem_sweep_run(self._plan, ops._ptr(d_CM), ops._ptr(d_mapG), ops._ptr(d_mapS), ops._ptr(d_G0),
-                                     ops._ptr(d_dG), ops._ptr(d_s0), ops._ptr(d_ds),
-                                     None if mid is None else mid.ctypes.data_as(C.POINTER(C.c_int32)),
-                                     ops._ptr(d_streams), ops._ptr(d_emp), ops._ptr(d_gof), ops._ptr(d_extra),
-                                     ops._ptr(d_fc), ops._stream()))
+    @property
+    def chunks_total(self):
+        """Integrator launches (per tile group) of one whole run: the unit `advance` counts in."""
+        return int(lib.nrem_sweep_chunks_total(self._plan))
 
-    # -- host call (bench `e2e`, drivers): NumPy in, NumPy out ------------------------------------
-    def run(self, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False):
-        B, N, K, dev = self.B, self.N, self.K, self.dev
+    # -- device-resident calls (bench `value`): tensors already in HBM ----------------------------
+    def begin_device(self, d_CM, d_mapG, d_mapS, d_G0, d_dG, d_s0, d_ds, map_id, d_streams, homogeneous=-1):
+        """Stage the inputs of a run and rewind the plan (nrem_sweep_begin).  homogeneous: True/False when the caller knows
+        whether every map entry is exactly 1, -1 to let the library find out (one stream synchronisation)."""
+        mid = None
+        if map_id is not None:
+            mid = np.ascontiguousarray(map_id, dtype=np.int32)
+            if mid.shape != (self.B,):
+                raise ValueError(f"map_id must have shape ({self.B},), got {mid.shape}")
+            if mid.min() < 0 or mid.max() >= self.n_maps:
+                raise ValueError(f"map_id values must lie in [0, {self.n_maps})")
+        for name, t, n in (("G0", d_G0, self.B), ("dG", d_dG, self.B), ("sigma0", d_s0, self.B), ("dsigma", d_ds, self.B),
+                           ("streams", d_streams, self.B), ("CM", d_CM, self.N * self.N), ("mapG", d_mapG, self.n_maps * self.N),
+                           ("mapS", d_mapS, self.n_maps * self.N)):
+            if t.numel() != n:
+                raise ValueError(f"{name} has {t.numel()} elements, expected {n}")
+        hint = -1 if homogeneous in (-1, None) else int(bool(homogeneous))
+        self._held = (d_CM, d_mapG, d_mapS, d_G0, d_dG, d_s0, d_ds, d_streams)       # alive until the kernels have read them
+        with torch.cuda.device(self.dev):
+            check(lib.nrem_sweep_begin(self._plan, ops._ptr(d_CM), ops._ptr(d_mapG), ops._ptr(d_mapS), ops._ptr(d_G0),
+                                       ops._ptr(d_dG), ops._ptr(d_s0), ops._ptr(d_ds),
+                                       None if mid is None else mid.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       ops._ptr(d_streams), hint, ops._stream()))
+
+    def advance(self, max_chunks=None):
+        """Enqueue up to max_chunks integrator launches (default: all that are left); returns how many are left."""
+        left = C.c_int64()
+        n = self.chunks_total if max_chunks is None else int(max_chunks)
+        with torch.cuda.device(self.dev):
+            check(lib.nrem_sweep_advance(self._plan, n, C.byref(left), ops._stream()))
+        return int(left.value)
+
+    def feed_samples(self, E):
+        """Test hook: feed stored E samples [rows, N, B] (float32; what run() records) to the plan's BOLD / filter / spectrum
+        kernels instead of integrating.  Consecutive calls continue the series; all but the last must bring a multiple of
+        chunk_samples rows."""
+        E = np.ascontiguousarray(E, dtype=np.float32)
+        if E.ndim != 3 or E.shape[1:] != (self.N, self.B):
+            raise ValueError(f"E must be [rows, {self.N}, {self.B}], got {E.shape}")
+        Bs = (self.B + TILE - 1) // TILE * TILE
+        with torch.cuda.device(self.dev):
+            d = torch.zeros((E.shape[0], self.N, Bs), dtype=torch.float32, device=self.dev)
+            d[:, :, :self.B] = ops.to_device(E, torch.float32, self.dev)
+            check(lib.nrem_sweep_feed_samples(self._plan, ops._ptr(d), E.shape[0], ops._stream()))
+            torch.cuda.current_stream().synchronize()          # d is freed on return
+
+    def finish_device(self, d_emp, d_gof, d_extra, d_fc=None):
+        if d_emp.numel() != self.K * self.N * self.N or d_gof.numel() != self.B * self.K * 4:
+            raise ValueError("emp / gof have the wrong size")
+        with torch.cuda.device(self.dev):
+            check(lib.nrem_sweep_finish(self._plan, ops._ptr(d_emp), ops._ptr(d_gof), ops._ptr(d_extra), ops._ptr(d_fc), ops._stream()))
+
+    def run_device(self, d_CM, d_mapG, d_mapS, d_G0, d_dG, d_s0, d_ds, map_id, d_streams, d_emp, d_gof, d_extra, d_fc=None,
+                   homogeneous=-1):
+        self.begin_device(d_CM, d_mapG, d_mapS, d_G0, d_dG, d_s0, d_ds, map_id, d_streams, homogeneous)
+        self.advance()
+        self.finish_device(d_emp, d_gof, d_extra, d_fc)
+
+    # -- host calls (bench `e2e`, drivers): NumPy in, NumPy out -----------------------------------
+    def begin(self, CM, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None):
+        """Upload the inputs of one run (pinned H2D) and rewind the plan to Euler step 0."""
+        B, N, dev = self.B, self.N, self.dev
         f64 = torch.float64
         mapG = np.ones((1, N)) if mapG is None else np.atleast_2d(np.asarray(mapG, dtype=np.float64))
         mapS = np.ones((1, N)) if mapS is None else np.atleast_2d(np.asarray(mapS, dtype=np.float64))
         if mapG.shape != (self.n_maps, N) or mapS.shape != (self.n_maps, N):
             raise ValueError(f"maps must be [{self.n_maps}, {N}]")
+        CM = np.asarray(CM, dtype=np.float64)
+        if CM.shape != (N, N):
+            raise ValueError(f"CM must be [{N}, {N}], got {CM.shape}")
+        streams = np.asarray(streams, dtype=np.uint64)
+        if streams.shape != (B,):
+            raise ValueError(f"streams must have shape ({B},), got {streams.shape}")
+        per_sim = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (B,))) for a in (G0, dG, sigma0, dsigma)]
+        homo = bool(np.all(mapG == 1.0) and np.all(mapS == 1.0))
+        with torch.cuda.device(dev):
+            d_CM = ops.to_device(CM, f64, dev)
+            d_mG, d_mS = ops.to_device(mapG, f64, dev), ops.to_device(mapS, f64, dev)
+            d_par = [ops.to_device(a, f64, dev) for a in per_sim]
+            d_st = ops._u64(streams, dev)
+            self.begin_device(d_CM, d_mG, d_mS, d_par[0], d_par[1], d_par[2], d_par[3], map_id, d_st, homogeneous=homo)
+        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in [d_CM, d_mG, d_mS, d_st] + d_par)
+
+    def finish(self, emp, want_fc=False):
+        """Backward filter pass, FC, GoF and observables of the completed run; downloads the result table (D2H)."""
+        B, N, K, dev = self.B, self.N, self.K, self.dev
+        f64 = torch.float64
         emp = np.asarray(emp, dtype=np.float64)
         if emp.shape != (K, N, N):
             raise ValueError(f"emp must be [{K}, {N}, {N}]")
-        per_sim = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (B,))) for a in (G0, dG, sigma0, dsigma)]
         with torch.cuda.device(dev):
-            d_CM = ops.to_device(np.asarray(CM, dtype=np.float64), f64, dev)
-            d_mG, d_mS, d_emp = ops.to_device(mapG, f64, dev), ops.to_device(mapS, f64, dev), ops.to_device(emp, f64, dev)
-            d_par = [ops.to_device(a, f64, dev) for a in per_sim]
-            d_st = ops._u64(streams, dev)
+            d_emp = ops.to_device(emp, f64, dev)
             d_gof = torch.empty((B, K, 4), dtype=f64, device=dev)
             d_extra = torch.empty((B, 4), dtype=f64, device=dev)
             d_fc = torch.empty((B, N, N), dtype=f64, device=dev) if want_fc else None
-            self.run_device(d_CM, d_mG, d_mS, d_par[0], d_par[1], d_par[2], d_par[3], map_id, d_st, d_emp, d_gof, d_extra, d_fc)
+            self.finish_device(d_emp, d_gof, d_extra, d_fc)
             extra = d_extra.cpu().numpy()
             out = {"gof": d_gof.cpu().numpy(), "mean": extra[:, 0], "sync": extra[:, 1], "meta": extra[:, 2], "peakfreq": extra[:, 3]}
             if want_fc:
                 out["fc"] = d_fc.cpu().numpy()
-        self.h2d_bytes = sum(int(t.numel() * t.element_size()) for t in [d_CM, d_mG, d_mS, d_emp, d_st] + d_par)
+        self._held = None
+        self.h2d_bytes = getattr(self, "h2d_bytes", 0) + int(d_emp.numel() * 8)
         self.d2h_bytes = int(d_gof.numel() * 8 + B * 4 * 8 + (d_fc.numel() * 8 if want_fc else 0))
         return out
+
+    def run(self, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False):
+        self.begin(CM, G0, dG, sigma0, dsigma, streams, mapG, mapS, map_id)
+        self.advance()
+        return self.finish(emp, want_fc)
 
 
 def sweep_gof(p, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False, **plan_kw):

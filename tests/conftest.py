@@ -20,7 +20,8 @@ def load_golden(name):
 
 @pytest.fixture(scope="session")
 def aal90():
-    return load_golden("aal90_inputs.npz")
+    """The reference's input DATA (SC, empirical FCs, NA/ACh maps): data/aal90_inputs.npz, not a golden output."""
+    return np.load(os.path.join(ROOT, "data", "aal90_inputs.npz"), allow_pickle=False)
 
 
 @pytest.fixture(scope="session")

@@ -6,7 +6,7 @@ Run in the build container only (needs /root/reference, numba, scipy):
 
 What it does
 ------------
-* aal90_inputs.npz      — the reference's DATA inputs (SC, 4 empirical FCs, NA/ACh maps).
+* ../../data/aal90_inputs.npz — the reference's DATA inputs (SC, 4 empirical FCs, NA/ACh maps); input data, not a golden output.
 * wc_short_*.npz        — trajectories of the reference's own ``run()`` (numba) with its
                           noise stream seeded inside numba (``np.random.seed`` in an @njit
                           function; that stream equals RandomState(s).normal(0, 0.2, (steps, N))
@@ -78,7 +78,7 @@ emp = {s: np.loadtxt(f"{REF}/empirical/mean_mat_{s}_8dic24.txt") for s in ("W", 
 maps = {n: np.load(f"{REF}/empirical/maps/{n}.npy").astype(np.float64) for n in
         ("DIST_VAChT_feobv_hc18_aghourian", "DIST_LC_proj",
          "SHUFFLED_SYMM_DIST_VAChT_feobv_hc18_aghourian", "SHUFFLED_SYMM_DIST_LC_proj")}
-save("aal90_inputs.npz", SC=struct, W=emp["W"], N1=emp["N1"], N2=emp["N2"], N3=emp["N3"],
+save(os.path.join("..", "..", "data", "aal90_inputs.npz"), SC=struct, W=emp["W"], N1=emp["N1"], N2=emp["N2"], N3=emp["N3"],
      map_ACh=maps["DIST_VAChT_feobv_hc18_aghourian"], map_NA=maps["DIST_LC_proj"],
      map_ACh_shuf=maps["SHUFFLED_SYMM_DIST_VAChT_feobv_hc18_aghourian"], map_NA_shuf=maps["SHUFFLED_SYMM_DIST_LC_proj"])
 

@@ -268,7 +268,11 @@ def test_sweep_pipeline_vs_oracle(kernel, bold_f32, aal90, oracle_lib):
         assert rel[0].max() < (5e-3 if kernel == "tc" else 5e-4)
         E = Eg[:, :, k].astype(np.float64)
         FC = bold_oracle.fc(bold_oracle.filt_decimate(oracle_lib.bold_sim(E, 0.04), 10, 100, 0.04))
-        assert np.max(np.abs(FC - out["fc"][k])) < (2e-2 if bold_f32 else 1e-6)        # (b)
+        # (b) float64 BOLD state: the stages agree to 1e-6.  float32 BOLD state: this run keeps 1 s of signal, of which the band-pass
+        # passes ~1e-3, so float32 rounding of the Balloon-Windkessel state is amplified ~1e3-fold in FC — a property of the
+        # shortened test, not of the kernel: at the reference's length the same kernel is held to 1e-4
+        # (test_full_length_tail_matches_oracle below).
+        assert np.max(np.abs(FC - out["fc"][k])) < (2e-2 if bold_f32 else 1e-6)
         g = np.array([bold_oracle.get_all_metrics(out["fc"][k], emp[j]) for j in range(4)])
         assert np.allclose(g, out["gof"][k], atol=1e-9)
         assert abs(out["mean"][k] - out["fc"][k].mean()) < 1e-12
@@ -289,6 +293,103 @@ def test_tcgen05_contraction(passes, tol, aal90):
     out = ops.selftest_tc_coupling(E, SC, passes=passes)
     exact = E.astype(np.float64) @ SC.astype(np.float64).T
     assert np.max(np.abs(out - exact)) < tol * np.max(np.abs(exact))
+
+
+def test_full_length_tail_matches_oracle(aal90, oracle_lib):
+    """Deterministic parity of the kernels the bench times, at the reference's sizes: 300 000 stored samples x 90 nodes,
+    Neq = 2000, decimation 1000 (netwWilsonCowanPlastic.py:140-158, whole_sweep_both.py:79-96).
+
+    E samples come from the production integrator itself (float32, full recording phase).  They go through (1) the fused sweep
+    (`SweepPlan.run` on the same Philox streams: integrator -> bold_filter_chunk_kernel<float> -> filt_backward -> FC -> GoF ->
+    Kuramoto -> Welch, the benched configuration), (2) the stored-samples hook of the plan with float32 and (3) float64
+    Balloon-Windkessel state, and are compared with the oracle chain (C Balloon-Windkessel, SciPy filtfilt, np.corrcoef,
+    utils.get_all_metrics, utils.kuramoto, scipy.signal.welch) fed with the SAME samples.
+    north_star: FC within 1e-4 absolute."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle
+    n1, n2, n3 = 10_000, 200_000, 6_000_000                    # shortened transient, FULL recording phase
+    p = ops.make_params(90, n1, n2, n3, P=0.4, rhoE=0.18, seed=31)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    B = 2
+    G0, s0 = np.full(B, 0.16), np.full(B, 7.68)
+    dG, ds = np.array([0.0, 0.18]), np.array([0.0, -0.02])
+    streams = np.array([11, 12], dtype=np.uint64)
+    Eg, _ = ops.integrate_f32(p, aal90["SC"], G0, dG, s0, ds, streams=streams, kernel="auto")
+    assert Eg.shape == (300_000, 90, B)
+    plan = sweep.SweepPlan(p, B, bold_f32=True, peakfreq=True)
+    runs = {"fused f32": plan.run(aal90["SC"], emp, G0, dG, s0, ds, streams, want_fc=True)}
+    plan.begin(aal90["SC"], G0, dG, s0, ds, streams)
+    for r0 in range(0, 300_000, 10_000):
+        plan.feed_samples(Eg[r0:r0 + 10_000])
+    runs["fed f32"] = plan.finish(emp, want_fc=True)
+    plan.close()
+    plan = sweep.SweepPlan(p, B, bold_f32=False, peakfreq=True)
+    plan.begin(aal90["SC"], G0, dG, s0, ds, streams)
+    for r0 in range(0, 300_000, 10_000):
+        plan.feed_samples(Eg[r0:r0 + 10_000])
+    runs["fed f64"] = plan.finish(emp, want_fc=True)
+    plan.close()
+    assert np.array_equal(runs["fused f32"]["fc"], runs["fed f32"]["fc"])          # same kernels, same samples
+    for k in range(B):
+        E = Eg[:, :, k].astype(np.float64)
+        bold = bold_oracle.filt_decimate(oracle_lib.bold_sim(E, 0.04), 1000, 2000, 0.04)
+        assert bold.shape == (298, 90)
+        FC = bold_oracle.fc(bold)
+        sync, meta = bold_oracle.kuramoto(bold)
+        gof = np.array([bold_oracle.get_all_metrics(FC, emp[j]) for j in range(4)])
+        peak = bold_oracle.welch_peak(E)
+        for name, out in runs.items():
+            tol_fc = 1e-6 if name == "fed f64" else 1e-4
+            err = np.max(np.abs(out["fc"][k] - FC))
+            print(f"{name} sim {k}: max |FC - oracle| = {err:.2e}, sync {abs(out['sync'][k] - sync):.1e}, meta {abs(out['meta'][k] - meta):.1e}")
+            assert err < tol_fc, (name, k, err)
+            assert abs(out["sync"][k] - sync) < 1e-4 and abs(out["meta"][k] - meta) < 1e-4
+            assert np.max(np.abs(out["gof"][k] - gof)) < (1e-5 if name == "fed f64" else 2e-3)      # eucl. distance sums 4005 entries
+            assert abs(out["mean"][k] - FC.mean()) < tol_fc
+            assert out["peakfreq"][k] == peak
+
+
+def test_sliced_run_equals_one_call(aal90):
+    """nrem_sweep_begin / advance / finish (what bench.py times slice by slice): cutting a run into pieces changes nothing, bit
+    for bit, with one stream and with tile-group streams, homogeneous and with maps."""
+    import torch
+    from nremmodfc_b200 import ops, sweep
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    p = ops.make_params(90, 300, 1100, 5000, P=0.4, rhoE=0.18, seed=17)
+    kw = dict(Neq=40, bold_downsamp=5, chunk_samples=20, bold_f32=True, peakfreq=True, welch_nperseg=80)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(2)
+    for B, hetero in ((200, False), (200, True), ((sms + 2) * 128, False)):
+        dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+        streams = rng.integers(0, 2 ** 60, B).astype(np.uint64)
+        maps = dict(mapG=aal90["map_ACh"] / aal90["map_ACh"].mean(), mapS=aal90["map_NA"] / aal90["map_NA"].mean()) if hetero else {}
+        plan = sweep.SweepPlan(p, B, **kw)
+        one = plan.run(aal90["SC"], emp, 0.16, dG, 7.68, ds, streams, want_fc=True, **maps)
+        total = plan.chunks_total
+        assert total == 1 + 3 + 13                                   # ceil(300/400) + ceil(1100/400) + ceil(5000/400)
+        plan.begin(aal90["SC"], 0.16, dG, 7.68, ds, streams, **maps)
+        left, seen = total, []
+        for n in (1, 2, 0, 5, 3, 100):
+            left = plan.advance(n)
+            seen.append(left)
+        assert seen == [16, 14, 14, 9, 6, 0]
+        two = plan.finish(emp, want_fc=True)
+        plan.close()
+        for key in ("gof", "fc", "mean", "sync", "meta", "peakfreq"):
+            assert np.array_equal(one[key], two[key]), (B, hetero, key)
+        assert np.isfinite(one["gof"]).all() and np.isfinite(one["peakfreq"]).all()
+    # finishing a run that is not complete is an error, not a wrong table
+    from nremmodfc_b200._lib import NremError
+    plan = sweep.SweepPlan(p, 4, **kw)
+    plan.begin(aal90["SC"], 0.16, np.zeros(4), 7.68, np.zeros(4), np.arange(4, dtype=np.uint64))
+    plan.advance(3)
+    with pytest.raises(NremError):
+        plan.finish(emp)
+    with pytest.raises(ValueError):
+        plan.begin(aal90["SC"], 0.16, np.zeros(4), 7.68, np.zeros(4), np.arange(3, dtype=np.uint64))       # short streams array
+    with pytest.raises(ValueError):
+        plan.begin(aal90["SC"], 0.16, np.zeros(4), 7.68, np.zeros(4), np.arange(4, dtype=np.uint64), map_id=np.array([0, 0, 0, 1]))
+    plan.close()
 
 
 def test_sweep_with_more_tiles_than_sms(aal90):

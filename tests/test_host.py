@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(built):
     assert declared == set(_lib.ABI_SYMBOLS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.nrem_abi_version() == 1
+    assert _lib.lib.nrem_abi_version() == 2
     nm = subprocess.run(["nm", "-D", "--defined-only", built], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", nm), f"{name} is not an exported text symbol"
@@ -253,3 +253,57 @@ def test_many_seeds_batch_assembly(monkeypatch, aal90):
     assert set(rec) == {"Hin_sim", "Hse_sim", "Hin_node_sim", "Hse_node_sim", "sFC"}
     assert rec["sFC"].min() >= 0.0 and rec["Hin_node_sim"].shape == (90,)           # HMA clips negatives in place, as the reference does
     assert many_seeds.OPTIMALS["homo"]["N3"] == (0.16, -0.04, 7.68, 0.04) and many_seeds.OPTIMALS["shuf"]["N1"] == (0.16, 0.0, 7.68, 0.04)
+
+
+def _staged():
+    return os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "whole_sweep_both.py"))
+
+
+@pytest.mark.skipif(not _staged(), reason="baseline/_ref is not staged (build() copies it where /root/reference exists)")
+def test_unmodified_drivers_reach_the_cuda_library_through_compat(built, tmp_path):
+    """whole_sweep_both.py / whole_sweep_both_maps.py / run_many_seeds.py, byte-identical copies, with compat/ on PYTHONPATH: every
+    import and data path resolves and the first `wc.run()` lands in the CUDA library — which, on a box without a GPU, must refuse
+    (NremError) instead of computing anything on the CPU.  (With a GPU the same scripts produce rows: tests/test_gpu_drivers.py.)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_drivers.py")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_drivers as drv
+    cwd = drv._workdir(tmp_path)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT]), SLURM_ARRAY_TASK_ID="0", SLURM_ARRAY_TASK_MAX="199")
+    procs = [subprocess.Popen([sys.executable, s], cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for s in ("whole_sweep_both.py", "whole_sweep_both_maps.py", "run_many_seeds.py")]
+    for pr in procs:
+        out, _ = pr.communicate(timeout=300)
+        assert pr.returncode != 0
+        assert "NremError: no CUDA device visible" in out and "wc.run()" in out, out[-1500:]
+
+
+@pytest.mark.skipif(not _staged(), reason="baseline/_ref is not staged")
+def test_reference_arm_runs_the_unmodified_numba_module(built):
+    """bench.py --impl reference / cpu_baseline: the reference's own netwWilsonCowanPlastic.py (numba) from baseline/_ref, with the
+    oracle's shims for its two absent dependencies; and the oracle's restatement agrees with it on a seeded stream."""
+    pytest.importorskip("numba")
+    code = r'''
+import sys, numpy as np, numba
+sys.path.insert(0, %r)
+import bench
+from oracle import refshim, wc_oracle
+bench._ref_init()
+rec, run, tail = bench._ref_sim(0.001)
+assert rec >= 0 and run > 0
+wc = bench._REF["wc"]
+assert wc.__file__.startswith(refshim.REF_DIR) and hasattr(wc.run, "recompile")
+@numba.njit
+def nseed(s):
+    np.random.seed(s)
+wc.timeTrans1, wc.timeTrans2, wc.timeSim, wc.time = np.arange(30.), np.arange(50.), np.arange(120.), np.arange(6.)
+wc.run.recompile(); nseed(11)
+Y = wc.run()
+nz = np.random.RandomState(11).normal(0, 0.2, size=(200, 90))
+Yo = wc_oracle.run(wc.CM, 0.16, 7.68, 30, 50, 120, noise=nz, p=wc_oracle.params(P=0.4, rhoE=0.18))
+assert Y.shape == Yo.shape == (6, 3, 90) and np.max(np.abs(Y - Yo) / np.abs(Yo)) < 1e-11
+print("ok")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 from nremmodfc_b200 import ops  # noqa: E402
 from oracle import cwrap, wc_oracle  # noqa: E402
 
-d = np.load(os.path.join(ROOT, "tests", "golden", "aal90_inputs.npz"))
+d = np.load(os.path.join(ROOT, "data", "aal90_inputs.npz"))
 n1, n2, n3 = 200, 800, 10000
 p = ops.make_params(90, n1, n2, n3, P=0.4, rhoE=0.18, seed=9)
 po = wc_oracle.params(P=0.4, rhoE=0.18)

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nremmodfc_b200 import ops  # noqa: E402
 
-d = np.load(os.path.join(ROOT, "tests", "golden", "aal90_inputs.npz"))
+d = np.load(os.path.join(ROOT, "data", "aal90_inputs.npz"))
 tiles = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 B = tiles * 128
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4000

@@ -47,7 +47,7 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
-    d = np.load(os.path.join(ROOT, "tests", "golden", "aal90_inputs.npz"))
+    d = np.load(os.path.join(ROOT, "data", "aal90_inputs.npz"))
     stats = np.load(os.path.join(ROOT, "tests", "golden", "sweep_cell_stats.npz"))
     emp = np.stack([d[s] for s in ("W", "N1", "N2", "N3")])
     norm = lambda m: m / m.mean()                                                   # whole_sweep_both_maps.py:54,62

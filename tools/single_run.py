@@ -12,7 +12,7 @@ import netwWilsonCowanPlastic as wc  # noqa: E402
 import utils  # noqa: E402
 from scipy import signal  # noqa: E402
 
-d = np.load(os.path.join(ROOT, "tests", "golden", "aal90_inputs.npz"))
+d = np.load(os.path.join(ROOT, "data", "aal90_inputs.npz"))
 wc.P, wc.rhoE, wc.CM = 0.4, 0.18, d["SC"]
 wc.tTrans1, wc.tTrans2, tstop = 1, 400, 600
 wc.timeTrans1 = np.arange(0, wc.tTrans1, wc.dtSim)
