@@ -124,7 +124,8 @@ int nrem_kuramoto_f64(const double* bold, int B, int64_t J, int N, double* sync_
 typedef struct nrem_sweep_plan nrem_sweep_plan;   /* opaque; owns device scratch */
 
 typedef struct nrem_sweep_opts {
-    int32_t kernel;          /* 0 = auto, 1 = CUDA-core coupling, 2 = tcgen05 (TF32) coupling, 3 = tcgen05 3xTF32 */
+    int32_t kernel;          /* 0 = auto, 1 = CUDA-core coupling, 2 = tcgen05 (TF32) coupling, 3 = tcgen05 3xTF32,            */
+                             /* 5 / 6 = node-lane tcgen05 3xTF32 with 32 / 16 simulations per CTA (see nrem_sweep_kernel)       */
     int32_t bold_f32;        /* 1 = Balloon-Windkessel state in float32 (default 0 = float64)      */
     int32_t chunk_samples;   /* stored samples per launch of the integrator (0 = default)           */
     int32_t want_fc;         /* 1 = also return the FC matrices                                      */
@@ -165,6 +166,15 @@ int nrem_sweep_run(nrem_sweep_plan* plan, const double* CM, const double* mapG, 
  *             simulation, never crossing a phase boundary; a whole run has nrem_sweep_chunks_total of them) plus the
  *             BOLD/filter launches that consume their samples; *h_chunks_left (host, may be NULL) = launches still to go.
  *   finish  : backward filter pass, FC, GoF, sync/meta/peakfreq of a run whose integration is complete (outputs as nrem_sweep_run). */
+/* Per-node vectors for the scalar model parameters of the NEXT runs of this plan ("Any of them can be redefined as a vector of
+ * length nnodes", netwWilsonCowanPlastic.py:21): node_params = device [NREM_NODE_PARAMS, N] in the order of nrem_wc_run_f64_ex
+ * (copied into the plan), or NULL to go back to the scalars of nrem_wc_params.  Selects the node-lane kernel.            */
+int nrem_sweep_set_node_params(nrem_sweep_plan* plan, const double* node_params, void* stream);
+/* The integrator kernel the plan resolved to (1 CUDA-core, 2 tcgen05 TF32, 3 tcgen05 3xTF32: 128 simulations per CTA, a
+ * thread = one simulation x 24 nodes; 5 / 6 node-lane tcgen05 3xTF32: 32 / 16 simulations per CTA, a thread = one node x 8 / 4
+ * simulations, nnodes <= 128).  opts.kernel = 0 picks 6 or 5 for batches too small to fill the SMs with 128-simulation tiles,
+ * for nnodes > 96 and for per-node parameter tables, else 3.                                                                   */
+int nrem_sweep_kernel(const nrem_sweep_plan* plan);
 int nrem_sweep_begin(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,
                      const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                      const int32_t* h_map_id, const uint64_t* streams, int homogeneous, void* stream);
@@ -187,12 +197,19 @@ int nrem_sweep_set_profiling(nrem_sweep_plan* plan, int on);
 int nrem_sweep_get_profile(nrem_sweep_plan* plan, double* h_out);
 
 /* Test hooks for the sweep's integrator: advance B simulations n1+n2+n3 steps with kernel
- * variant `kernel` and return the float32 E samples [nrec, N, Bpad] (Bpad = B rounded up to
+ * variant `kernel` (codes of nrem_sweep_opts.kernel) and return the float32 E samples [nrec, N, Bpad] (Bpad = B rounded up to
  * NREM_TILE_SIMS, simulation fastest) and the final state [3, N, Bpad].                        */
 int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG,
                              const double* mapS, const double* G0, const double* dG, const double* sigma0,
                              const double* dsigma, const int32_t* h_map_id, const uint64_t* streams, int B,
                              int n_maps, int64_t nrec, float* E_samples, float* final_state, void* stream);
+
+/* Same with a per-node parameter table (node_params: NULL or device [NREM_NODE_PARAMS, N], node-lane kernels only). */
+int nrem_sweep_integrate_f32_ex(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG,
+                                const double* mapS, const double* G0, const double* dG, const double* sigma0,
+                                const double* dsigma, const int32_t* h_map_id, const uint64_t* streams,
+                                const double* node_params, int B, int n_maps, int64_t nrec, float* E_samples,
+                                float* final_state, void* stream);
 
 /* Large connectomes (BASELINE configs[4]; netwWilsonCowanPlastic.py:64-68 allows any nnodes): integrates B simulations of
  * 16 <= nnodes <= 8192 nodes with one launch per Euler step (tcgen05 GEMM of the whole batch with the node update fused

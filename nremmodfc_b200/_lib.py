@@ -14,8 +14,8 @@ ABI_SYMBOLS = [
     "nrem_abi_version", "nrem_last_error", "nrem_device_count", "nrem_wc_run_f64", "nrem_wc_run_f64_ex", "nrem_wc_derivative_f64",
     "nrem_bold_sim_f64", "nrem_filt_scratch_bytes", "nrem_filtfilt_decimate_f64", "nrem_fc_f64", "nrem_gof_f64", "nrem_kuramoto_f64",
     "nrem_sweep_create", "nrem_sweep_destroy", "nrem_sweep_device_bytes", "nrem_sweep_run",
-    "nrem_sweep_begin", "nrem_sweep_chunks_total", "nrem_sweep_advance", "nrem_sweep_finish", "nrem_sweep_feed_samples",
-    "nrem_sweep_integrate_f32", "nrem_big_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
+    "nrem_sweep_set_node_params", "nrem_sweep_kernel", "nrem_sweep_begin", "nrem_sweep_chunks_total", "nrem_sweep_advance", "nrem_sweep_finish", "nrem_sweep_feed_samples",
+    "nrem_sweep_integrate_f32", "nrem_sweep_integrate_f32_ex", "nrem_big_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
 ]
 
 
@@ -66,6 +66,8 @@ lib.nrem_sweep_device_bytes.restype = _i64
 lib.nrem_sweep_device_bytes.argtypes = [_vp]
 lib.nrem_sweep_run.argtypes = [_vp] + [_vp] * 7 + [C.POINTER(C.c_int32), _vp, _vp, _vp, _vp, _vp, _vp]
 lib.nrem_sweep_begin.argtypes = [_vp] + [_vp] * 7 + [C.POINTER(C.c_int32), _vp, _i, _vp]
+lib.nrem_sweep_set_node_params.argtypes = [_vp, _vp, _vp]
+lib.nrem_sweep_kernel.argtypes = [_vp]
 lib.nrem_sweep_chunks_total.restype = _i64
 lib.nrem_sweep_chunks_total.argtypes = [_vp]
 lib.nrem_sweep_advance.argtypes = [_vp, _i64, C.POINTER(_i64), _vp]
@@ -73,6 +75,7 @@ lib.nrem_sweep_finish.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
 lib.nrem_sweep_feed_samples.argtypes = [_vp, _vp, _i64, _vp]
 lib.nrem_big_integrate_f32.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 8 + [_i, _i64, _vp, _vp, _vp, _vp]
 lib.nrem_sweep_integrate_f32.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 7 + [C.POINTER(C.c_int32), _vp, _i, _i, _i64, _vp, _vp, _vp]
+lib.nrem_sweep_integrate_f32_ex.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 7 + [C.POINTER(C.c_int32), _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]
 lib.nrem_measure_fma_peak.argtypes = [C.POINTER(_d), C.POINTER(_d)]
 lib.nrem_sweep_set_profiling.argtypes = [_vp, _i]
 lib.nrem_sweep_get_profile.argtypes = [_vp, C.POINTER(_d)]

@@ -101,13 +101,13 @@ __global__ void __launch_bounds__(kFcThreads) fc_f64_kernel(const double* bold, 
 }
 
 // fc [B][N][N], emp [K][N][N] -> gof [B][K][4] = (corr, euc, ssim, new_metric), meanfc [B].
-// dynamic smem: (2*N*N + 40) doubles
+// dynamic smem: (2*N*N + 40) doubles with emp_smem (N <= 118), else (N*N + 40) and the target is read from global memory
 __global__ void __launch_bounds__(256) gof_f64_kernel(const double* fc, const double* emp, int K, int N, double data_range,
-                                                      double* gof, double* meanfc) {
+                                                      double* gof, double* meanfc, int emp_smem) {
     extern __shared__ double smg[];
     double* S = smg;
-    double* Em = smg + N * N;
-    double* red = smg + 2 * N * N;
+    double* Ems = smg + N * N;
+    double* red = smg + (emp_smem ? 2 : 1) * N * N;
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const int NN = N * N;
     for (int k = tid; k < NN; k += nt) S[k] = fc[(size_t)b * NN + k];
@@ -124,7 +124,11 @@ __global__ void __launch_bounds__(256) gof_f64_kernel(const double* fc, const do
     const double cov_norm = 49.0 / 48.0;                      // sample covariance (use_sample_covariance=True)
     for (int kt = 0; kt < K; ++kt) {
         __syncthreads();
-        for (int k = tid; k < NN; k += nt) Em[k] = emp[(size_t)kt * NN + k];
+        const double* Em = emp + (size_t)kt * NN;
+        if (emp_smem) {
+            for (int k = tid; k < NN; k += nt) Ems[k] = emp[(size_t)kt * NN + k];
+            Em = Ems;
+        }
         __syncthreads();
         // strict upper triangle, two-pass Pearson (np.corrcoef of the two flattened vectors)
         double ss = 0.0, se = 0.0;

@@ -12,6 +12,7 @@
 #include "wc_batch.cuh"
 #include "wc_f64.cuh"
 #include "wc_tc.cuh"
+#include "wc_node.cuh"
 #include "wc_big.cuh"
 #include "welch.cuh"
 
@@ -247,10 +248,11 @@ int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, doubl
                  double* gof, double* meanfc, void* stream) {
     NREM_REQUIRE(fc && emp && gof, "null array");
     NREM_REQUIRE(B >= 1 && K >= 1, "bad shape");
-    NREM_REQUIRE(N >= 7 && N <= 118, "gof supports 7 <= N <= 118");
-    const size_t sm = sizeof(double) * (2 * (size_t)N * N + 40);
+    NREM_REQUIRE(N >= 7 && N <= 128, "gof supports 7 <= N <= 128");
+    const int emp_smem = N <= 118 ? 1 : 0;          // both matrices fit shared memory up to N = 118; above, the target is read through L1/L2
+    const size_t sm = sizeof(double) * ((emp_smem ? 2 : 1) * (size_t)N * N + 40);
     NREM_CUDA(cudaFuncSetAttribute(gof_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    gof_f64_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(fc, emp, K, N, data_range, gof, meanfc);
+    gof_f64_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(fc, emp, K, N, data_range, gof, meanfc, emp_smem);
     NREM_LAUNCHED();
     return NREM_OK;
 }
@@ -309,6 +311,11 @@ struct nrem_sweep_plan {
     double *bold_dec, *fc;
     double *obs, *hilb;            // [3][B] observables scratch, [J] Hilbert kernel (filled at create)
     int* dflag;                    // homogeneity flag (begin with homogeneous = -1)
+    int kernel;                    // resolved integrator kernel (1..3, 5, 6)
+    int tile_sims;                 // simulations per CTA of that kernel (128, 32 or 16)
+    int ld;                        // padded node count of the staged SC / maps (96 or 128)
+    double* node_par;              // [NREM_NODE_PARAMS][N] per-node parameter table, valid when has_node_par
+    bool has_node_par;
     // pinned host staging of the per-tile map ids, and the event after which it may be overwritten
     int32_t* h_tm;
     cudaEvent_t tm_done;
@@ -349,21 +356,36 @@ static BatchConst make_const(const nrem_wc_params& p) {
     return c;
 }
 
-static int resolve_kernel(int kernel) {
-    if (kernel == 0) return 3;      // auto = tcgen05 3xTF32
-    return kernel;
+// Simulations per CTA of an integrator kernel: the simulation-lane kernels (1 = CUDA-core, 2/3 = tcgen05) use tiles of 128,
+// the node-lane kernel (wc_node.cuh) tiles of 32 (kernel 5) or 16 (kernel 6).
+static int kernel_tile_sims(int kernel) { return kernel == 5 ? 32 : kernel == 6 ? 16 : kTile; }
+
+// kernel 0 = auto.  The time loop is sequential, so a batch that cannot fill the SMs with 128-simulation tiles is faster on
+// small tiles (measured per-step times: wc_node.cuh / DESIGN.md); connectomes above 96 nodes and per-node parameter tables
+// exist only on the node-lane kernel.
+static int resolve_kernel(int kernel, int N, int64_t B, bool node_par) {
+    if (kernel != 0) return kernel;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static const int cut32 = []() { const char* e = getenv("NREM_NODE_WAVES"); return e ? atoi(e) : 2; }();
+    if (B <= (int64_t)16 * sms) return 6;
+    if (N > kNPad || node_par || B <= (int64_t)32 * sms * cut32) return 5;
+    return 3;      // tcgen05 3xTF32, 128 simulations per CTA
 }
 
 // Launch one piece of the integrator.
 static int launch_integrator(int kernel, const BatchArgs& A, int64_t tiles, cudaStream_t st) {
-    switch (resolve_kernel(kernel)) {
+    switch (kernel) {
         case 1:
             NREM_CUDA(cudaFuncSetAttribute(wc_batch_v0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV0SmemBytes));
             wc_batch_v0_kernel<<<(unsigned)tiles, kBatchThreads, kV0SmemBytes, st>>>(A);
             break;
         case 2:
         case 3:
-            return launch_wc_tc(resolve_kernel(kernel), A.homo != 0, A, tiles, st);
+            return launch_wc_tc(kernel, A.homo != 0, A, tiles, st);
+        case 5:
+        case 6:
+            return launch_wc_node(kernel_tile_sims(kernel), A, tiles, st);
         default:
             return fail(NREM_ERR_ARG, "unknown integrator kernel%s%s");
     }
@@ -388,7 +410,7 @@ __global__ void fill_strided_f64_kernel(double* dst, int64_t n, int64_t stride, 
 static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, const double* CM, const double* mapG,
                         const double* mapS, const double* G0, const double* dG, const double* s0, const double* ds,
                         const int32_t* h_map_id, const uint64_t* streams, const StagePtrs& d, cudaStream_t st, int homo_hint,
-                        int* dflag, int32_t* h_tm, cudaEvent_t tm_done, int* homo) {
+                        int* dflag, int32_t* h_tm, cudaEvent_t tm_done, int* homo, int ld) {
     const int N = p.nnodes;
     std::vector<int32_t> tm_local;
     int32_t* tm = h_tm;
@@ -405,9 +427,9 @@ static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, 
     NREM_CUDA(cudaMemcpyAsync(d.tile_map, tm, (size_t)(Bs / kTile) * 4, cudaMemcpyHostToDevice, st));
     if (h_tm) { if (tm_done) NREM_CUDA(cudaEventRecord(tm_done, st)); }
     else NREM_CUDA(cudaStreamSynchronize(st));
-    stage_sc_kernel<<<(kNPad * kNPad + 255) / 256, 256, 0, st>>>(CM, N, d.SCp);
+    stage_sc_kernel<<<(ld * ld + 255) / 256, 256, 0, st>>>(CM, N, ld, d.SCp);
     NREM_LAUNCHED();
-    stage_maps_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(mapG, mapS, n_maps, N, d.mapG, d.mapS);
+    stage_maps_kernel<<<(n_maps * ld + 255) / 256, 256, 0, st>>>(mapG, mapS, n_maps, N, ld, d.mapG, d.mapS);
     NREM_LAUNCHED();
     if (homo_hint >= 0) {
         *homo = homo_hint ? 1 : 0;
@@ -416,7 +438,7 @@ static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, 
         if (!flag) NREM_CUDA(cudaMalloc(&flag, sizeof(int)));
         cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
         if (e == cudaSuccess) {
-            maps_not_all_ones_kernel<<<(n_maps * kNPad + 255) / 256, 256, 0, st>>>(d.mapG, d.mapS, n_maps, N, flag);
+            maps_not_all_ones_kernel<<<(n_maps * ld + 255) / 256, 256, 0, st>>>(d.mapG, d.mapS, n_maps, N, ld, flag);
             ++g_launches;
             e = cudaGetLastError();
         }
@@ -436,14 +458,20 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     if (int rc = check_params(p)) return rc;
     NREM_REQUIRE(o && plan, "null argument");
     NREM_REQUIRE(B >= 1 && n_maps >= 1 && K >= 1, "bad shape");
-    NREM_REQUIRE(p->nnodes >= 7 && p->nnodes <= kNPad, "the sweep supports 7 <= nnodes <= 96");
+    NREM_REQUIRE(p->nnodes >= 7 && p->nnodes <= 128, "the sweep supports 7 <= nnodes <= 128");
     NREM_REQUIRE(o->bold_downsamp >= 1 && o->Neq >= 0, "bad BOLD options");
+    NREM_REQUIRE(o->kernel >= 0 && o->kernel <= 6 && o->kernel != 4, "kernel must be 0 (auto), 1, 2, 3, 5 or 6");
+    NREM_REQUIRE(p->nnodes <= kNPad || o->kernel == 0 || o->kernel >= 5, "more than 96 nodes need the node-lane kernel (kernel 0, 5 or 6)");
     nrem_sweep_plan* P = new (std::nothrow) nrem_sweep_plan();
     if (!P) return fail(NREM_ERR_ARG, "out of host memory%s%s");
     P->p = *p; P->o = *o; P->B = B; P->n_maps = n_maps; P->K = K; P->N = p->nnodes; P->dev = nullptr;
     P->prof_on = false; P->ev_used = 0; P->span_used = 0; P->gfork = nullptr; P->last_groups = 1;
     P->h_tm = nullptr; P->tm_done = nullptr; P->begun = false; P->fed_rows = 0; P->homo = 0;
     P->cur = IntegCursor{0, 0, 0, 1};
+    P->node_par = nullptr; P->has_node_par = false;
+    P->kernel = resolve_kernel(o->kernel, p->nnodes, B, false);
+    P->tile_sims = kernel_tile_sims(P->kernel);
+    P->ld = p->nnodes > kNPad ? 128 : kNPad;
     P->Bs = round_up(B, kTile); P->tiles = P->Bs / kTile;
     P->T = (p->n3 + p->downsamp - 1) / p->downsamp;
     P->Tf = P->T - o->Neq;
@@ -477,9 +505,10 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     int64_t off = 0;
     auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
     const int64_t o_state = take(4 * 4 * (int64_t)N * P->Bs);
-    const int64_t o_sc = take(4 * kNPad * kNPad);
-    const int64_t o_mg = take(4 * (int64_t)n_maps * kNPad);
-    const int64_t o_ms = take(4 * (int64_t)n_maps * kNPad);
+    const int64_t o_sc = take(4 * (int64_t)P->ld * P->ld);
+    const int64_t o_mg = take(4 * (int64_t)n_maps * P->ld);
+    const int64_t o_ms = take(4 * (int64_t)n_maps * P->ld);
+    const int64_t o_np = take(8 * (int64_t)NREM_NODE_PARAMS * N);
     const int64_t o_par = take(4 * 4 * P->Bs);
     const int64_t o_tm = take(4 * P->tiles);
     const int64_t o_st = take(8 * P->Bs);
@@ -500,6 +529,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     char* base = (char*)P->dev;
     P->state = (float*)(base + o_state); P->SCp = (float*)(base + o_sc); P->mapG = (float*)(base + o_mg);
     P->mapS = (float*)(base + o_ms); P->par = (float*)(base + o_par); P->tile_map = (int32_t*)(base + o_tm);
+    P->node_par = (double*)(base + o_np);
     P->streams = (uint64_t*)(base + o_st); P->Ebuf = (float*)(base + o_eb); P->bw_state = base + o_bw;
     double* ptab_dev;
     P->S = carve_filt((double*)(base + o_fs), P->nth, P->J, o->bold_downsamp, &ptab_dev);
@@ -591,13 +621,18 @@ static int launch_bold_chunk(nrem_sweep_plan* plan, const float* Echunk, int row
 // groups of <= 8, each with its own stream and its own chain  K1(chunk 0) -> K2(chunk 0) -> K1(chunk 1) ...
 // Chains are independent, so whenever one group's CTAs retire, waiting CTAs of any other group take the
 // SMs: the sweep costs tiles/SMs "rounds" instead of ceil(tiles/SMs).
-static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, int64_t Bs, int chunk_samples,
-                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st, int homo, IntegCursor& cur, int64_t max_chunks) {
+static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, int64_t B, int64_t Bs, int chunk_samples,
+                     float* Ebuf_all, nrem_sweep_plan* plan, cudaStream_t st, int homo, IntegCursor& cur, int64_t max_chunks, int ld,
+                     const double* node_par) {
     BatchArgs A;
     A.c = make_const(p);
     A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
     A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp; A.homo = homo; A.zero = 0;
-    const int64_t tiles = Bs / kTile;
+    A.ld = ld; A.node_par = node_par; A.dtSim = p.dtSim;
+    // simulation-lane kernels: all Bs/128 tiles (padding simulations repeat the last real one); node-lane kernel: only the
+    // tiles that hold real simulations
+    const int tsz = kernel_tile_sims(kernel);
+    const int64_t tiles = tsz == kTile ? Bs / kTile : (B + tsz - 1) / tsz;
     int dev = 0, sms = 148;
     NREM_CUDA(cudaGetDevice(&dev));
     NREM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -651,7 +686,7 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
             if (e1) NREM_CUDA(cudaEventRecord(e1, gs[g]));
             if (ph == 2 && plan) {
                 const float* Echunk = d.Ebuf + ring_row0 * (int64_t)plan->N * Bs;
-                if (int rc = launch_bold_chunk(plan, Echunk, rows, row_base, t0 * kTile, (t1 - t0) * kTile, gs[g])) return rc;
+                if (int rc = launch_bold_chunk(plan, Echunk, rows, row_base, t0 * tsz, (t1 - t0) * tsz, gs[g])) return rc;
             }
         }
         cur.i0 += n; cur.step += n; cur.first = 0;
@@ -686,6 +721,20 @@ struct SpanTimer {
     ~SpanTimer() { if (end) cudaEventRecord(end, st); }
 };
 
+int nrem_sweep_set_node_params(nrem_sweep_plan* P, const double* node_params, void* stream) {
+    NREM_REQUIRE(P, "plan is null");
+    if (!node_params) { P->has_node_par = false; P->kernel = resolve_kernel(P->o.kernel, P->N, P->B, false); P->tile_sims = kernel_tile_sims(P->kernel); return NREM_OK; }
+    NREM_REQUIRE(P->o.kernel == 0 || P->o.kernel >= 5, "per-node parameter tables need the node-lane kernel (kernel 0, 5 or 6)");
+    NREM_CUDA(cudaMemcpyAsync(P->node_par, node_params, sizeof(double) * NREM_NODE_PARAMS * (size_t)P->N, cudaMemcpyDeviceToDevice,
+                              (cudaStream_t)stream));
+    P->has_node_par = true;
+    P->kernel = resolve_kernel(P->o.kernel, P->N, P->B, true);
+    P->tile_sims = kernel_tile_sims(P->kernel);
+    return NREM_OK;
+}
+
+int nrem_sweep_kernel(const nrem_sweep_plan* plan) { return plan ? plan->kernel : -1; }
+
 int nrem_sweep_begin(nrem_sweep_plan* P, const double* CM, const double* mapG, const double* mapS,
                      const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                      const int32_t* h_map_id, const uint64_t* streams, int homogeneous, void* stream) {
@@ -698,7 +747,7 @@ int nrem_sweep_begin(nrem_sweep_plan* P, const double* CM, const double* mapG, c
     StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
     if (P->welchP) NREM_CUDA(cudaMemsetAsync(P->welchP, 0, 4 * P->Bs * (size_t)(P->welch.M + 1), st));
     if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st,
-                              homogeneous, P->dflag, P->h_tm, P->tm_done, &P->homo)) return rc;
+                              homogeneous, P->dflag, P->h_tm, P->tm_done, &P->homo, P->ld)) return rc;
     P->cur = IntegCursor{0, 0, 0, 1};
     P->fed_rows = 0;
     P->begun = true;
@@ -714,7 +763,8 @@ int nrem_sweep_advance(nrem_sweep_plan* P, int64_t max_chunks, int64_t* h_chunks
     SpanTimer span(P, st);
     StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
     if (max_chunks > 0)
-        if (int rc = integrate(P->p, P->o.kernel, d, P->Bs, P->chunk_samples, nullptr, P, st, P->homo, P->cur, max_chunks)) return rc;
+        if (int rc = integrate(P->p, P->kernel, d, P->B, P->Bs, P->chunk_samples, nullptr, P, st, P->homo, P->cur, max_chunks, P->ld,
+                               P->has_node_par ? P->node_par : nullptr)) return rc;
     if (h_chunks_left) {
         const int64_t cs = (int64_t)P->chunk_samples * P->p.downsamp;
         const int64_t ns[3] = {P->p.n1, P->p.n2, P->p.n3};
@@ -831,19 +881,32 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
                              const double* mapS, const double* G0, const double* dG, const double* sigma0,
                              const double* dsigma, const int32_t* h_map_id, const uint64_t* streams, int B,
                              int n_maps, int64_t nrec, float* E_samples, float* final_state, void* stream) {
+    return nrem_sweep_integrate_f32_ex(p, kernel, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, nullptr, B, n_maps, nrec,
+                                       E_samples, final_state, stream);
+}
+
+int nrem_sweep_integrate_f32_ex(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG,
+                                const double* mapS, const double* G0, const double* dG, const double* sigma0,
+                                const double* dsigma, const int32_t* h_map_id, const uint64_t* streams,
+                                const double* node_params, int B, int n_maps, int64_t nrec, float* E_samples,
+                                float* final_state, void* stream) {
     if (int rc = check_params(p)) return rc;
     NREM_REQUIRE(CM && mapG && mapS && G0 && dG && sigma0 && dsigma && streams, "null array");
     NREM_REQUIRE(B >= 1 && n_maps >= 1, "bad shape");
-    NREM_REQUIRE(p->nnodes >= 1 && p->nnodes <= kNPad, "the sweep supports nnodes <= 96");
+    const int kern = resolve_kernel(kernel, p->nnodes, B, node_params != nullptr);
+    NREM_REQUIRE(!node_params || kern >= 5, "per-node parameter tables need the node-lane kernel");
+    NREM_REQUIRE(kern == 1 || kern == 2 || kern == 3 || kern == 5 || kern == 6, "kernel must be auto, fma, tc, tc3, node32 or node16");
+    NREM_REQUIRE(p->nnodes >= 1 && p->nnodes <= (kern >= 5 ? 128 : kNPad), "the simulation-lane kernels support nnodes <= 96, the node-lane kernel <= 128");
     NREM_REQUIRE(!E_samples || nrec >= (p->n3 + p->downsamp - 1) / p->downsamp, "nrec too small");
     NREM_REQUIRE(final_state, "final_state is required");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = p->nnodes;
+    const int ld = N > kNPad ? 128 : kNPad;
     const int64_t Bs = round_up(B, kTile);
     // scratch: everything except the state (which is the caller's final_state buffer)
     int64_t off = 0;
     auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
-    const int64_t o_sc = take(4 * kNPad * kNPad), o_mg = take(4 * (int64_t)n_maps * kNPad), o_ms = take(4 * (int64_t)n_maps * kNPad);
+    const int64_t o_sc = take(4 * (int64_t)ld * ld), o_mg = take(4 * (int64_t)n_maps * ld), o_ms = take(4 * (int64_t)n_maps * ld);
     const int64_t o_par = take(4 * 4 * Bs), o_tm = take(4 * (Bs / kTile)), o_st = take(8 * Bs);
     const int kDummyRows = 64;
     const int64_t o_dummy = take(E_samples ? 256 : 4 * (int64_t)kDummyRows * N * Bs);
@@ -854,15 +917,16 @@ int nrem_sweep_integrate_f32(const nrem_wc_params* p, int kernel, const double* 
     StagePtrs d{(float*)(base + o_st4), (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
                 (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
     int homo = 0;
-    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, -1, nullptr, nullptr, nullptr, &homo);
+    cudaMemsetAsync(base + o_st4, 0, (size_t)(4 * 4 * (int64_t)N * Bs), st);      // padding simulations the node-lane kernel skips
+    int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, -1, nullptr, nullptr, nullptr, &homo, ld);
     IntegCursor cur{0, 0, 0, 1};
     const int64_t all = (int64_t)1 << 60;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     if (rc == NREM_OK) {
         cudaEventRecord(t0, st);
-        if (E_samples) rc = integrate(*p, kernel, d, Bs, 1 << 20, E_samples, nullptr, st, homo, cur, all);
-        else rc = integrate(*p, kernel, d, Bs, kDummyRows, nullptr, nullptr, st, homo, cur, all);   // samples go to a scratch ring
+        if (E_samples) rc = integrate(*p, kern, d, B, Bs, 1 << 20, E_samples, nullptr, st, homo, cur, all, ld, node_params);
+        else rc = integrate(*p, kern, d, B, Bs, kDummyRows, nullptr, nullptr, st, homo, cur, all, ld, node_params);   // samples go to a scratch ring
         cudaEventRecord(t1, st);
         if (rc == NREM_OK) {
             const int64_t n = (int64_t)N * Bs;

@@ -31,9 +31,12 @@ struct BatchConst {
 struct BatchArgs {
     BatchConst c;
     float* state;              // [4][N][Bs]: E, I, a_ie base, a_ie delta (a_ie = base + delta, see wc_tc.cuh)
-    const float* SCp;          // [96][96] zero padded
-    const float* mapG;         // [n_maps][96]
-    const float* mapS;         // [n_maps][96]
+    const float* SCp;          // [ld][ld] zero padded (ld = 96; 128 for the node-lane kernel with N > 96)
+    const float* mapG;         // [n_maps][ld]
+    const float* mapS;         // [n_maps][ld]
+    int ld;
+    const double* node_par;    // node-lane kernel only: NULL or [NREM_NODE_PARAMS][N] per-node parameter table (device)
+    double dtSim;              // node-lane kernel only (per-node dtSim/tau constants)
     const float* par;          // [4][Bs]: G0, dG, sigma0, dsigma
     const int32_t* tile_map;   // [Bs/128]
     const uint64_t* streams;   // [Bs]
@@ -185,24 +188,24 @@ __global__ void combine_state_kernel(const float* st4, int64_t n, float* out3) {
 }
 
 // ---- host-side staging kernels (float64 API arrays -> padded float32 device layout) ----------
-__global__ void stage_sc_kernel(const double* CM, int N, float* SCp) {
+__global__ void stage_sc_kernel(const double* CM, int N, int ld, float* SCp) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= kNPad * kNPad) return;
-    const int i = k / kNPad, j = k % kNPad;
+    if (k >= ld * ld) return;
+    const int i = k / ld, j = k % ld;
     SCp[k] = (i < N && j < N) ? (float)CM[(size_t)i * N + j] : 0.f;
 }
-__global__ void stage_maps_kernel(const double* mapG, const double* mapS, int n_maps, int N, float* oG, float* oS) {
+__global__ void stage_maps_kernel(const double* mapG, const double* mapS, int n_maps, int N, int ld, float* oG, float* oS) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_maps * kNPad) return;
-    const int m = k / kNPad, i = k % kNPad;
+    if (k >= n_maps * ld) return;
+    const int m = k / ld, i = k % ld;
     oG[k] = i < N ? (float)mapG[(size_t)m * N + i] : 0.f;
     oS[k] = i < N ? (float)mapS[(size_t)m * N + i] : 0.f;
 }
 // flag[0] (zeroed by the caller) becomes 1 when some real map entry differs from 1
-__global__ void maps_not_all_ones_kernel(const float* mG, const float* mS, int n_maps, int N, int* flag) {
+__global__ void maps_not_all_ones_kernel(const float* mG, const float* mS, int n_maps, int N, int ld, int* flag) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_maps * kNPad) return;
-    if ((k % kNPad) < N && (mG[k] != 1.0f || mS[k] != 1.0f)) flag[0] = 1;
+    if (k >= n_maps * ld) return;
+    if ((k % ld) < N && (mG[k] != 1.0f || mS[k] != 1.0f)) flag[0] = 1;
 }
 __global__ void stage_par_kernel(const double* G0, const double* dG, const double* s0, const double* ds,
                                  const uint64_t* streams, int B, int64_t Bs, float* par, uint64_t* st) {

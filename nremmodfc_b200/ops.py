@@ -91,6 +91,21 @@ def _per_node(x, B, N, name):
 NODE_PARAMS = ("a_ee", "a_ei", "a_ii", "tauE", "tauI", "P", "rhoE", "rE", "rI", "mu", "sigmaI", "a_ie_0")     # NREM_NODE_PARAMS order
 
 
+def node_param_table(p, node_params):
+    """{name: scalar or length-N vector} -> [NREM_NODE_PARAMS, N] float64 table (names not given: the scalar of `p`)."""
+    N = p.nnodes
+    unknown = set(node_params) - set(NODE_PARAMS)
+    if unknown:
+        raise ValueError(f"not per-node parameters: {sorted(unknown)} (allowed: {NODE_PARAMS})")
+    npar = np.empty((len(NODE_PARAMS), N))
+    for k, name in enumerate(NODE_PARAMS):
+        v = np.asarray(node_params.get(name, getattr(p, name)), dtype=np.float64)
+        if v.ndim > 1 or (v.ndim == 1 and v.shape[0] != N):
+            raise ValueError(f"{name} must be a scalar or a vector of length {N}")
+        npar[k] = v
+    return npar
+
+
 def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=True, node_params=None, device=None):
     """run() of netwWilsonCowanPlastic.py:86-137 for B simulations (float64).
 
@@ -116,17 +131,7 @@ def wc_run(p, CM, G, sigmaE, B=1, streams=None, noise=None, nrec=None, want_Y=Tr
             raise ValueError(f"noise must be [1 or {B}, {steps}, {N}], got {noise.shape}")
         nb = noise.shape[0]
         d_noise = to_device(noise, torch.float64, dev)
-    npar = None
-    if node_params:
-        unknown = set(node_params) - set(NODE_PARAMS)
-        if unknown:
-            raise ValueError(f"not per-node parameters: {sorted(unknown)} (allowed: {NODE_PARAMS})")
-        npar = np.empty((len(NODE_PARAMS), N))
-        for k, name in enumerate(NODE_PARAMS):
-            v = np.asarray(node_params.get(name, getattr(p, name)), dtype=np.float64)
-            if v.ndim > 1 or (v.ndim == 1 and v.shape[0] != N):
-                raise ValueError(f"{name} must be a scalar or a vector of length {N}")
-            npar[k] = v
+    npar = node_param_table(p, node_params) if node_params else None
     with torch.cuda.device(dev):
         d_CM, d_G, d_sg = (to_device(x, torch.float64, dev) for x in (CM, G, sg))
         d_np = None if npar is None else to_device(npar, torch.float64, dev)
@@ -249,12 +254,14 @@ def kuramoto(bold, device=None):
     return (float(out[0, 0]), float(out[0, 1])) if sq else (out[:, 0], out[:, 1])
 
 
-KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3, "tcb": 4}
+KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3, "tcb": 4, "node32": 5, "node16": 6}
+KERNEL_NAMES = {v: k for k, v in KERNELS.items()}
 
 
 def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=None, streams=None, kernel="fma",
-                  record=True, device=None):
-    """Test hook: the sweep's float32 integrator alone.  Returns (E samples [nrec, N, B] or None, final [3, N, B])."""
+                  record=True, node_params=None, device=None):
+    """Test hook: the sweep's float32 integrator alone (kernel: a name of KERNELS; node_params: per-node vectors, node-lane
+    kernels only).  Returns (E samples [nrec, N, B] or None, final [3, N, B])."""
     dev = _device(device)
     N = p.nnodes
     G0 = np.atleast_1d(np.asarray(G0, dtype=np.float64))
@@ -279,10 +286,11 @@ def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=No
         d_st = _u64(streams, dev)
         d_E = torch.empty((max(nrec, 1), N, Bs), dtype=torch.float32, device=dev) if record and nrec > 0 else None
         d_fin = torch.empty((3, N, Bs), dtype=torch.float32, device=dev)
-        check(lib.nrem_sweep_integrate_f32(C.byref(p), KERNELS[kernel], _ptr(d_CM), _ptr(d_mG), _ptr(d_mS), _ptr(d[0]),
-                                           _ptr(d[1]), _ptr(d[2]), _ptr(d[3]),
-                                           None if mid is None else mid.ctypes.data_as(C.POINTER(C.c_int32)),
-                                           _ptr(d_st), B, mapG.shape[0], nrec, _ptr(d_E), _ptr(d_fin), _stream()))
+        d_np = None if not node_params else to_device(node_param_table(p, node_params), torch.float64, dev)
+        check(lib.nrem_sweep_integrate_f32_ex(C.byref(p), KERNELS[kernel], _ptr(d_CM), _ptr(d_mG), _ptr(d_mS), _ptr(d[0]),
+                                              _ptr(d[1]), _ptr(d[2]), _ptr(d[3]),
+                                              None if mid is None else mid.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              _ptr(d_st), _ptr(d_np), B, mapG.shape[0], nrec, _ptr(d_E), _ptr(d_fin), _stream()))
         E = d_E[:, :, :B].cpu().numpy() if d_E is not None else None
         return E, d_fin[:, :, :B].cpu().numpy()
 

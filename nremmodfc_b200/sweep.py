@@ -156,6 +156,25 @@ class SweepPlan:
             pass
 
     @property
+    def kernel_name(self):
+        """The integrator kernel the plan resolved to: "tc3" (128 simulations per CTA), "node32" / "node16" (node-lane kernel,
+        32 / 16 simulations per CTA: small batches, nnodes > 96, per-node parameter tables), "fma", "tc"."""
+        return ops.KERNEL_NAMES[int(lib.nrem_sweep_kernel(self._plan))]
+
+    def set_node_params(self, node_params=None):
+        """Per-node vectors for any of ops.NODE_PARAMS ("Any of them can be redefined as a vector of length nnodes",
+        netwWilsonCowanPlastic.py:21) for the next runs: {name: length-N vector}; names not given keep the scalar of the plan's
+        parameters.  None / {} goes back to scalars."""
+        if not node_params:
+            check(lib.nrem_sweep_set_node_params(self._plan, None, ops._stream()))
+            return
+        table = ops.node_param_table(self.p, node_params)
+        with torch.cuda.device(self.dev):
+            d = ops.to_device(table, torch.float64, self.dev)
+            check(lib.nrem_sweep_set_node_params(self._plan, ops._ptr(d), ops._stream()))
+            torch.cuda.current_stream().synchronize()          # d is freed on return
+
+    @property
     def chunks_total(self):
         """Integrator launches (per tile group) of one whole run: the unit `advance` counts in."""
         return int(lib.nrem_sweep_chunks_total(self._plan))
@@ -265,18 +284,20 @@ class SweepPlan:
         self.d2h_bytes = int(d_gof.numel() * 8 + B * 4 * 8 + (d_fc.numel() * 8 if want_fc else 0))
         return out
 
-    def run(self, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False):
+    def run(self, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False, node_params=None):
+        if node_params is not None:
+            self.set_node_params(node_params)
         self.begin(CM, G0, dG, sigma0, dsigma, streams, mapG, mapS, map_id)
         self.advance()
         return self.finish(emp, want_fc)
 
 
-def sweep_gof(p, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False, **plan_kw):
+def sweep_gof(p, CM, emp, G0, dG, sigma0, dsigma, streams, mapG=None, mapS=None, map_id=None, want_fc=False, node_params=None, **plan_kw):
     """One-shot convenience wrapper: build a plan for len(streams) simulations, run it, free it."""
     B = len(np.atleast_1d(streams))
     n_maps = 1 if mapG is None else np.atleast_2d(mapG).shape[0]
     plan = SweepPlan(p, B, n_maps=n_maps, K=np.asarray(emp).shape[0], **plan_kw)
     try:
-        return plan.run(CM, emp, G0, dG, sigma0, dsigma, streams, mapG, mapS, map_id, want_fc)
+        return plan.run(CM, emp, G0, dG, sigma0, dsigma, streams, mapG, mapS, map_id, want_fc, node_params)
     finally:
         plan.close()

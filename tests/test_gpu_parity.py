@@ -722,3 +722,143 @@ def test_every_node_parameter_as_a_vector(aal90):
         for k, v in saved.items():
             setattr(wc, k, v)
     assert np.array_equal(Yd, Y[0])
+
+
+# ---- node-lane integrator (csrc/wc_node.cuh): small tiles, N <= 128, per-node parameter tables -------------------------------
+
+@pytest.mark.parametrize("hetero", [False, True])
+def test_node_lane_kernel_is_bit_identical_to_the_128_simulation_kernel(hetero, aal90):
+    """The low-latency kernel (a thread = one node x 8 or 4 simulations, transposed tcgen05 contraction, 32 / 16 simulations per
+    CTA) performs the same float32 operations on the same Philox stream as the throughput kernel (a thread = one simulation x 24
+    nodes): E samples and final state must agree bit for bit, across an a_ie recombination (global step 4096), for a ragged
+    batch, homogeneous and with NA/ACh maps."""
+    from nremmodfc_b200 import ops
+    p = ops.make_params(90, 300, 4000, 1200, P=0.4, rhoE=0.18, seed=12)
+    B = 200                                                    # run_many_seeds.py: 50 seeds x 4 states
+    rng = np.random.default_rng(4)
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    streams = rng.integers(0, 2 ** 62, B).astype(np.uint64)
+    kw = dict(streams=streams)
+    if hetero:
+        kw.update(mapG=np.stack([np.ones(90), aal90["map_ACh"] / aal90["map_ACh"].mean()]),
+                  mapS=np.stack([np.ones(90), aal90["map_NA"] / aal90["map_NA"].mean()]),
+                  map_id=np.r_[np.zeros(128, np.int32), np.ones(B - 128, np.int32)])
+    ref = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, kernel="tc3", **kw)
+    assert np.isfinite(ref[0]).all() and ref[0].shape == (60, 90, B)
+    for kernel in ("node32", "node16"):
+        got = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, kernel=kernel, **kw)
+        dE = np.max(np.abs(got[0] - ref[0]))
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (kernel, dE)
+
+
+@pytest.mark.parametrize("N,kernel", [(116, "node32"), (128, "node16"), (100, "auto"), (68, "node32")])
+def test_node_lane_kernel_other_parcellations_vs_oracle(N, kernel, oracle_lib):
+    """Connectomes up to 128 nodes (AAL116, Schaefer-100 ...; netwWilsonCowanPlastic.py:64-68 takes any len(CM)) on the node-lane
+    kernel against the float64 oracle on the same Philox streams, and the fused sweep's FC / GoF tail at that size."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle, wc_oracle
+    rng = np.random.default_rng(N)
+    SC = rng.uniform(size=(N, N)) * (rng.uniform(size=(N, N)) < 0.4)
+    SC = (SC + SC.T) / 2
+    np.fill_diagonal(SC, 0.0)
+    SC *= 2.5 / SC.sum(axis=1).mean()
+    n1, n2, n3 = 40, 80, 160
+    p = ops.make_params(N, n1, n2, n3, P=0.4, rhoE=0.18, seed=4)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    B = 70
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    mG, mS = rng.uniform(0.5, 1.5, (1, N)), rng.uniform(0.8, 1.2, (1, N))
+    streams = rng.integers(0, 2 ** 40, B).astype(np.uint64)
+    E, fin = ops.integrate_f32(p, SC, np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, streams=streams, kernel=kernel)
+    assert E.shape == (8, N, B)
+    for b in (0, 33, 69):
+        Yo, fo = wc_oracle.run(SC, 0.16 + dG[b] * mG[0], 7.68 + ds[b] * mS[0], n1, n2, n3, seed=4, streams=[int(streams[b])], p=po, return_final=True)
+        assert np.max(np.abs(E[:, :, b] - Yo[0, :, 0, :]) / np.abs(Yo[0, :, 0, :])) < 2e-4
+        assert np.max(np.abs(fin[:, :, b] - fo[0]) / np.abs(fo[0])) < 2e-4
+    # fused sweep at this size: stages after the integrator vs the oracle fed with the same samples
+    p2 = ops.make_params(N, 200, 800, 8000, P=0.4, rhoE=0.18, seed=5)
+    emp = np.stack([np.corrcoef(rng.normal(size=(N, 60)) + rng.normal(size=(1, 60))) for _ in range(4)])
+    plan = sweep.SweepPlan(p2, B, kernel=kernel, bold_f32=False, Neq=100, bold_downsamp=10, chunk_samples=64)
+    assert plan.kernel_name in ("node32", "node16")
+    out = plan.run(SC, emp, 0.16, dG, 7.68, ds, streams, mapG=mG, mapS=mS, want_fc=True)
+    plan.close()
+    Eg, _ = ops.integrate_f32(p2, SC, np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, streams=streams, kernel=plan_kernel(kernel, N))
+    for b in (0, 69):
+        bold = bold_oracle.filt_decimate(oracle_lib.bold_sim(Eg[:, :, b].astype(np.float64), 0.04), 10, 100, 0.04)
+        assert np.max(np.abs(bold_oracle.fc(bold) - out["fc"][b])) < 1e-6
+        g = np.array([bold_oracle.get_all_metrics(out["fc"][b], emp[j]) for j in range(4)])
+        assert np.allclose(g, out["gof"][b], atol=1e-9)
+
+
+def plan_kernel(kernel, N):
+    return "node16" if kernel == "auto" else kernel            # auto with 70 simulations: 16-simulation tiles
+
+
+def test_sweep_takes_every_node_parameter_as_a_vector(aal90, oracle_lib):
+    """"Any of them can be redefined as a vector of length nnodes" (netwWilsonCowanPlastic.py:21) on the batched path: all twelve
+    per-node vectors (the eleven model parameters and a_ie_0) through `node_params`, against the NumPy oracle whose expressions
+    broadcast; then through the fused sweep (same samples -> same FC as the oracle chain)."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle, wc_oracle
+    rng = np.random.default_rng(21)
+    N = 90
+    vec = {"a_ee": 3.5 + 0.2 * rng.random(N), "a_ei": 3.75 - 0.2 * rng.random(N), "a_ii": 0.1 * rng.random(N),
+           "tauE": 0.010 * (1 + 0.1 * rng.random(N)), "tauI": 0.020 * (1 + 0.1 * rng.random(N)), "P": 0.4 + 0.05 * rng.random(N),
+           "rhoE": 0.18 + 0.02 * rng.random(N), "rE": 0.5 + 0.05 * rng.random(N), "rI": 0.5 - 0.05 * rng.random(N),
+           "mu": 1.0 + 0.05 * rng.random(N), "sigmaI": 4.0 + 0.3 * rng.random(N), "a_ie_0": 2.5 + 0.2 * rng.random(N)}
+    n1, n2, n3 = 50, 100, 200
+    p = ops.make_params(N, n1, n2, n3, seed=8)
+    B = 40
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    mG, mS = aal90["map_ACh"] / aal90["map_ACh"].mean(), aal90["map_NA"] / aal90["map_NA"].mean()
+    streams = np.arange(B, dtype=np.uint64) + 3
+    E, fin = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG[None], mS[None], streams=streams,
+                               kernel="auto", node_params=vec)
+    po = wc_oracle.params(**vec)
+    for b in (0, 17, 39):
+        Yo, fo = wc_oracle.run(aal90["SC"], 0.16 + dG[b] * mG, 7.68 + ds[b] * mS, n1, n2, n3, seed=8, streams=[int(streams[b])], p=po,
+                               return_final=True)
+        assert np.max(np.abs(E[:, :, b] - Yo[0, :, 0, :]) / np.abs(Yo[0, :, 0, :])) < 2e-4
+        assert np.max(np.abs(fin[:, :, b] - fo[0]) / np.abs(fo[0])) < 2e-4
+    # scalars given as a "vector table" reproduce the scalar run bit for bit; a table changes the result
+    E0, _ = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG[None], mS[None], streams=streams, kernel="node16")
+    E1, _ = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG[None], mS[None], streams=streams, kernel="node16",
+                              node_params={"P": np.full(N, p.P)})
+    assert np.array_equal(E0, E1) and not np.allclose(E0, E)
+    with pytest.raises(Exception):
+        ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams=streams, kernel="tc3", node_params=vec)
+    # fused sweep
+    p2 = ops.make_params(N, 200, 800, 8000, seed=8)
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    out = sweep.sweep_gof(p2, aal90["SC"], emp, 0.16, dG, 7.68, ds, streams, mapG=mG[None], mapS=mS[None], want_fc=True, node_params=vec,
+                          bold_f32=False, Neq=100, bold_downsamp=10, chunk_samples=64)
+    Eg, _ = ops.integrate_f32(p2, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG[None], mS[None], streams=streams,
+                              kernel="auto", node_params=vec)
+    for b in (0, 39):
+        bold = bold_oracle.filt_decimate(oracle_lib.bold_sim(Eg[:, :, b].astype(np.float64), 0.04), 10, 100, 0.04)
+        assert np.max(np.abs(bold_oracle.fc(bold) - out["fc"][b])) < 1e-6
+
+
+def test_small_batch_uses_small_tiles_and_matches_the_large_batch(aal90):
+    """kernel="auto": a batch that cannot fill the SMs with 128-simulation tiles runs on 16- / 32-simulation tiles; the result
+    table is identical to the same simulations inside a big batch on the throughput kernel."""
+    import torch
+    from nremmodfc_b200 import ops, sweep
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    emp = np.stack([aal90[s] for s in ("W", "N1", "N2", "N3")])
+    p = ops.make_params(90, 100, 300, 2400, P=0.4, rhoE=0.18, seed=11)
+    kw = dict(Neq=40, bold_downsamp=5, chunk_samples=50, bold_f32=True)
+    rng = np.random.default_rng(6)
+    Bbig = 66 * sms * 2
+    dG, ds = rng.uniform(-0.1, 0.3, Bbig), rng.uniform(-0.2, 0.2, Bbig)
+    streams = rng.integers(0, 2 ** 60, Bbig).astype(np.uint64)
+    big = sweep.SweepPlan(p, Bbig, **kw)
+    assert big.kernel_name == "tc3"
+    ref = big.run(aal90["SC"], emp, 0.16, dG, 7.68, ds, streams)
+    big.close()
+    for B, name in ((200, "node16"), (20 * sms, "node32")):
+        plan = sweep.SweepPlan(p, B, **kw)
+        assert plan.kernel_name == name
+        out = plan.run(aal90["SC"], emp, 0.16, dG[:B], 7.68, ds[:B], streams[:B])
+        plan.close()
+        assert np.array_equal(out["gof"], ref["gof"][:B]) and np.array_equal(out["sync"], ref["sync"][:B])

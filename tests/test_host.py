@@ -186,6 +186,7 @@ def test_c_abi_argument_errors(built):
     assert lib.nrem_fc_f64(None, 1, 10, 90, one, None) == -1 and b"null" in lib.nrem_last_error()
     assert lib.nrem_fc_f64(one, 1, 10, 200, one, None) == -1 and b"N <= 128" in lib.nrem_last_error()
     assert lib.nrem_gof_f64(one, one, 1, 4, 3, 1.0, one, None, None) == -1
+    assert lib.nrem_gof_f64(one, one, 1, 4, 129, 1.0, one, None, None) == -1 and b"N <= 128" in lib.nrem_last_error()
     assert lib.nrem_bold_sim_f64(one, 0, 10, 90, 0.04, one, None) == -1
     assert lib.nrem_wc_run_f64(None, one, one, one, None, None, 1, 1, 1, None, one, None) == -1
     assert lib.nrem_wc_run_f64(C.byref(p), one, one, one, None, one, 3, 5, 1, None, one, None) == -1      # noise_batch not in {1, B}
@@ -198,7 +199,16 @@ def test_c_abi_argument_errors(built):
     o = _lib.SweepOpts()
     plan = C.c_void_p()
     pp = ops.make_params(200, 1, 1, 20)
-    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"nnodes <= 96" in lib.nrem_last_error()
+    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"nnodes <= 128" in lib.nrem_last_error()
+    pw = ops.make_params(120, 1, 1, 20)
+    o.kernel, o.bold_downsamp = 3, 10                          # the 128-simulation tcgen05 kernel is one 96-wide MMA tile
+    assert lib.nrem_sweep_create(C.byref(pw), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"node-lane" in lib.nrem_last_error()
+    o.kernel = 4
+    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1
+    assert lib.nrem_sweep_begin(None, *([one] * 7), None, one, 1, None) == -1
+    assert lib.nrem_sweep_advance(None, 1, None, None) == -1 and lib.nrem_sweep_finish(None, one, one, None, None, None) == -1
+    assert lib.nrem_sweep_feed_samples(None, one, 1, None) == -1 and lib.nrem_sweep_set_node_params(None, None, None) == -1
+    assert lib.nrem_sweep_chunks_total(None) == -1 and lib.nrem_sweep_kernel(None) == -1
     assert lib.nrem_sweep_run(None, *([one] * 7), None, one, one, one, one, None, None) == -1
     assert lib.nrem_selftest_tc_coupling(one, one, one, 2, 0, 0, 0, 0, 0, None) == -1
 
