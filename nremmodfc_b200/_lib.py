@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnremfc.so")
+# NREM_LIB_PATH: developer switch for kernel experiments (a variant build of the same C ABI, see build.build_variant)
+LIB_PATH = os.environ.get("NREM_LIB_PATH") or os.path.join(_HERE, "csrc", "libnremfc.so")
 
 ABI_SYMBOLS = [
     "nrem_abi_version", "nrem_last_error", "nrem_device_count", "nrem_wc_run_f64", "nrem_wc_run_f64_ex", "nrem_wc_derivative_f64",

@@ -30,5 +30,13 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """Experiment builds: csrc/libnremfc_<name>.so compiled with extra -D switches (load it with NREM_LIB_PATH)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    out = os.path.join(CSRC, f"libnremfc_{name}.so")
+    subprocess.check_call([nvcc] + FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES])
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

@@ -960,7 +960,15 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     cudaStream_t st = (cudaStream_t)stream;
     const int N = p->nnodes;
     const int Kpad = (int)round_up(N, 4 * kBigKS), KG = Kpad / 4, slices = (N + kBigNT - 1) / kBigNT;
-    const int64_t Bs = round_up(B, kTile);
+    // CTA pairs (cta_group::2, two 128-simulation tiles per M = 256 MMA) whenever the batch has an even number of tiles, or enough
+    // tiles that one padding tile is cheap; NREM_BIG_PAIR=0 / 1 forces the choice (read per call: tests run both).  The persistent
+    // cluster mode keeps single-CTA MMAs.
+    const char* env_pair = getenv("NREM_BIG_PAIR");
+    const char* env_persist = getenv("NREM_BIG_PERSIST");              // read per call so that tests can exercise both modes
+    const bool want_persist = env_persist ? atoi(env_persist) != 0 : false;   // measured 3-10 % slower than per-step launches + PDL
+    const int64_t tiles0 = round_up(B, kTile) / kTile;
+    const bool pair = !want_persist && (env_pair ? atoi(env_pair) != 0 : (tiles0 % 2 == 0 || tiles0 >= 9));
+    const int64_t Bs = round_up(B, pair ? 2 * kTile : kTile);
     const int tiles = (int)(Bs / kTile);
     const size_t nf4 = (size_t)tiles * KG * kTile;                      // float4 per state plane
     int64_t off = 0;
@@ -978,7 +986,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     auto body = [&]() -> int {
         NREM_CUDA(cudaMemsetAsync(dev, 0, (size_t)o_b, st));            // images and state: padding nodes stay zero for ever
         const size_t nb = (size_t)slices * KG * kBigNT * 4;
-        big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, mixed, (float*)(base + o_b));
+        big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, mixed, pair ? kBigNT / 2 : kBigNT, (float*)(base + o_b));
         NREM_LAUNCHED();
         big_stage_maps_kernel<<<(Kpad + 255) / 256, 256, 0, st>>>(mapG, mapS, N, Kpad, (float*)(base + o_mg), (float*)(base + o_ms));
         NREM_LAUNCHED();
@@ -995,25 +1003,24 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         A.I4 = (float4*)(base + o_i); A.ab4 = (float4*)(base + o_ab); A.ad4 = (float4*)(base + o_ad);
         A.par = (const float*)(base + o_par); A.streams = (const uint64_t*)(base + o_st);
         A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
-        A.Bs = Bs; A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
+        A.Bs = Bs; A.Bo = round_up(B, kTile); A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
         A.Ebuf = E_samples;
         const bool fullN = N % 8 == 0, homoN = A.homo != 0;
-        auto pick = [&](auto mode, auto persist) -> void (*)(const BigArgs) {
+        // variant: 0 = one launch per step, 1 = persistent cluster, 2 = one launch per step with CTA pairs
+        auto pick = [&](auto mode, auto variant) -> void (*)(const BigArgs) {
             constexpr int M = decltype(mode)::value;
-            constexpr bool P = decltype(persist)::value;
-            if (fullN) return homoN ? wc_big_step_kernel<M, true, true, P> : wc_big_step_kernel<M, true, false, P>;
-            return homoN ? wc_big_step_kernel<M, false, true, P> : wc_big_step_kernel<M, false, false, P>;
+            constexpr bool P = decltype(variant)::value == 1, PR = decltype(variant)::value == 2;
+            if (fullN) return homoN ? wc_big_step_kernel<M, true, true, P, PR> : wc_big_step_kernel<M, true, false, P, PR>;
+            return homoN ? wc_big_step_kernel<M, false, true, P, PR> : wc_big_step_kernel<M, false, false, P, PR>;
         };
-        auto pick2 = [&](auto persist) -> void (*)(const BigArgs) {
-            return k == 4 ? pick(std::integral_constant<int, 4>{}, persist)
-                 : k == 3 ? pick(std::integral_constant<int, 3>{}, persist) : pick(std::integral_constant<int, 1>{}, persist);
+        auto pick2 = [&](auto variant) -> void (*)(const BigArgs) {
+            return k == 4 ? pick(std::integral_constant<int, 4>{}, variant)
+                 : k == 3 ? pick(std::integral_constant<int, 3>{}, variant) : pick(std::integral_constant<int, 1>{}, variant);
         };
-        const int smem = k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>();
+        const int smem = pair ? (k == 2 ? big_smem_bytes<1, true>() : big_smem_bytes<3, true>()) : (k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>());
         const dim3 grid((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
         static const bool pdl = []() { const char* e = getenv("NREM_BIG_PDL"); return e ? atoi(e) != 0 : true; }();
-        const char* env_persist = getenv("NREM_BIG_PERSIST");          // read per call so that tests can exercise both modes
-        const bool want_persist = env_persist ? atoi(env_persist) != 0 : false;   // measured 3-10 % slower than per-step launches + PDL
         A.img[0] = img[0]; A.img[1] = img[1];
         A.n1 = (uint32_t)p->n1; A.n12 = (uint32_t)(p->n1 + p->n2); A.downsamp = p->downsamp;
         for (int ph = 0; ph < 3; ++ph) A.kA3[ph] = (float)(p->dtSim / p->tau_ip[ph]);
@@ -1023,7 +1030,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         // shared memory.  Correct (tests run both modes) but on B200 it measured 42.6-44.1 us/step against 41.3-42.2 for one launch
         // per step with programmatic dependent launch (tc3: 52-54 vs 47.7), so it is not the default.
         bool persist = want_persist && slices <= 8 && total > 0 && total <= 0x7fffffff;    // nsteps is an int
-        void (*kern_p)(const BigArgs) = pick2(std::true_type{});
+        void (*kern_p)(const BigArgs) = pick2(std::integral_constant<int, 1>{});
         cudaLaunchConfig_t cfgp = {};
         cudaLaunchAttribute atp[1];
         if (persist) {
@@ -1042,7 +1049,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             NREM_CUDA(cudaLaunchKernelEx(&cfgp, kern_p, A));
             NREM_LAUNCHED();
         } else {
-            void (*kern)(const BigArgs) = pick2(std::false_type{});
+            void (*kern)(const BigArgs) = pair ? pick2(std::integral_constant<int, 2>{}) : pick2(std::integral_constant<int, 0>{});
             NREM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             for (int64_t s = 0; s < total; ++s) {
                 const int ph = s < p->n1 ? 0 : (s < p->n1 + p->n2 ? 1 : 2);
@@ -1057,17 +1064,26 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
                 cfg.dynamicSmemBytes = (size_t)smem;
-                cudaLaunchAttribute at[1];
-                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                at[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+                cudaLaunchAttribute at[2];
+                int na = 0;
+                if (pair) {       // tiles 2p, 2p+1 of a node slice = one cluster = one CTA pair
+                    at[na].id = cudaLaunchAttributeClusterDimension;
+                    at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 2; at[na].val.clusterDim.z = 1;
+                    ++na;
+                }
+                if (pdl) {
+                    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    at[na].val.programmaticStreamSerializationAllowed = 1;
+                    ++na;
+                }
+                cfg.attrs = at; cfg.numAttrs = na;
                 NREM_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
                 NREM_LAUNCHED();
             }
         }
         NREM_CUDA(cudaEventRecord(t1, st));
-        const int64_t n = (int64_t)N * Bs;
-        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, Bs, mixed, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
+        const int64_t n = (int64_t)N * A.Bo;
+        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, A.Bo, mixed, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
                                                                       (const float*)A.ab4, (const float*)A.ad4, final_state);
         NREM_LAUNCHED();
         return NREM_OK;

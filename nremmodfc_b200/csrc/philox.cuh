@@ -1,4 +1,6 @@
-// Counter-based noise stream "nrem-philox-v1" (definition: oracle/philox.py).
+// Counter-based noise stream "nrem-philox-v2" (definition: oracle/philox.py): Philox4x32 with 7 rounds + Box-Muller.
+// (v1 used 10 rounds.  7 is the smallest round count of Philox4x32 that passes BigCrush — Salmon et al., SC'11, table 2 —
+// and the 3 rounds less are 6 % of the integrator's time: profiles/r02_kernel_variants.md.)
 // Replaces np.random.normal(0, sqdtD, size=N) of netwWilsonCowanPlastic.py:80, whose numba
 // MT19937 stream the reference never seeds.
 #pragma once
@@ -8,9 +10,13 @@ namespace nrem {
 
 struct Philox4 { uint32_t x, y, z, w; };
 
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#ifndef NREM_PHILOX_ROUNDS
+#define NREM_PHILOX_ROUNDS 7           // the stream definition (oracle/philox.py ROUNDS); other values are timing experiments only
+#endif
+
+__device__ __forceinline__ Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < NREM_PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0;

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_v0_kernel(const Bat
         } else { E[k] = 0.f; I[k] = 0.f; a[k] = 0.f; }
     }
     const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
-    const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
+    const float sg0 = __fmul_rn(-1.4426950408889634f, A.par[2 * A.Bs + sim]), dsg = __fmul_rn(-1.4426950408889634f, A.par[3 * A.Bs + sim]);
     const uint64_t strm = A.streams[sim];
     const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
     const int njg = (N + 3) >> 2;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) wc_batch_v0_kernel(const Bat
         for (int g = 0; g < kChunk / 4; ++g) {
             const int q = chunk * (kChunk / 4) + g;
             float z[4];
-            normals4f(philox4x32_10(step, (uint32_t)q, s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+            normals4f(philox4x32(step, (uint32_t)q, s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = 4 * g + j;

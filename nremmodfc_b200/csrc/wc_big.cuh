@@ -47,10 +47,17 @@ constexpr uint32_t kBigLBO_B = kBigNT * 16;
 constexpr uint32_t kBigTmemCols = 512;              // 0..255 coupling accumulator, 256..511 the coupling-free part of the sigmoid argument
 constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
-template <int MODE>
-constexpr uint32_t big_stage_bytes() { return (MODE == 1 ? 1u : 2u) * (kBigAStage + kBigBStage); }
-template <int MODE>
-constexpr int big_smem_bytes() { return (int)(kBigStages * big_stage_bytes<MODE>()) + 128; }
+// PAIR (cta_group::2): two CTAs of a cluster (two 128-simulation tiles, same node slice) execute ONE M = 256 MMA per K slice; each
+// CTA stages its own A tile and only HALF of the B tile (128 of the 256 output nodes), the tensor cores of the pair exchange the
+// halves.  Per SM and 16 input nodes that is 32 KB instead of 48 KB through the bulk-copy ring and shared memory, which buys a
+// 6-stage ring in the same shared memory.
+constexpr int kBigStagesPair = 6;
+template <int MODE, bool PAIR = false>
+constexpr uint32_t big_stage_bytes() { return (MODE == 1 ? 1u : 2u) * (kBigAStage + (PAIR ? kBigBStage / 2 : kBigBStage)); }
+template <int MODE, bool PAIR = false>
+constexpr int big_smem_bytes() { return (int)((PAIR ? kBigStagesPair : kBigStages) * big_stage_bytes<MODE, PAIR>()) + 256; }
+constexpr uint32_t kBigIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)((2 * kTile) >> 4) << 24);
+constexpr uint32_t kBigIdescBf16Pair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)((2 * kTile) >> 4) << 24);
 // kind::f16 instruction descriptor: D = F32, A = B = BF16 (format 1), K-major, N = 256, M = 128
 constexpr uint32_t kBigIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
@@ -58,6 +65,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- cta_group::2 (CTA pair) forms ----
+__device__ __forceinline__ void umma_tf32_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// arrive (release at cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();
+    } while (!ok);
+}
+
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ uint32_t bf16x2(float lo_elem, float hi_elem) {       // {lo_elem in bits 0..15, hi_elem in 16..31}, RN
     uint32_t r;
@@ -77,7 +122,8 @@ struct BigArgs {
     const uint64_t* streams;   // [Bs]
     const float* mapG;         // [4*KG]
     const float* mapS;
-    int64_t Bs;
+    int64_t Bs;                // simulations incl. padding tiles (a multiple of 128; of 256 for the CTA-pair kernel)
+    int64_t Bo;                // simulation stride of the OUTPUT arrays Ebuf / coup (B rounded up to 128, include/nremfc.h); Bo <= Bs
     int tiles, slices, KG;
     int homo;                  // maps are all ones
     uint32_t step;             // global Euler step index
@@ -156,19 +202,29 @@ struct BigQuad {             // state of one thread's four-node group
 // FULL: N is a multiple of 8, so no node of a processed 8-node group is padding.  HOMO: no per-node maps (G, sigma per simulation)
 // PERSIST: launched as thread-block clusters of `slices` CTAs (the node slices of one 128-simulation tile, which depend only on each
 //          other); the cluster runs A.nsteps Euler steps with one barrier.cluster per step instead of one launch per step.
-template <int MODE, bool FULL, bool HOMO, bool PERSIST>
+// PAIR   : launched as clusters (1, 2, 1): tiles 2p and 2p+1 of a node slice form a CTA pair (cta_group::2).  Rank 0 issues the
+//          M = 256 MMAs for both; every CTA streams its own A tile and its half of the B tile; the peer relays "my stage has
+//          landed" to the leader's full barrier; tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both.
+template <int MODE, bool FULL, bool HOMO, bool PERSIST, bool PAIR = false>
 __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
+    static_assert(!(PAIR && PERSIST), "the CTA-pair kernel is launched once per Euler step");
     constexpr bool SPLIT = MODE == 3;
     constexpr bool MIXED = MODE == 4;
-    constexpr uint32_t STAGE = (MODE == 1 ? 1u : 2u) * (kBigAStage + kBigBStage);
+    constexpr int NST = PAIR ? kBigStagesPair : kBigStages;
+    constexpr int BROWS = PAIR ? kBigNT / 2 : kBigNT;              // B rows (output nodes) this CTA holds in shared memory
+    constexpr uint32_t BSTAGE = (uint32_t)kBigKS * BROWS * 16;     // bytes of one FP32 B stage
+    constexpr uint32_t LBO_B = (uint32_t)BROWS * 16;
+    constexpr uint32_t STAGE = (MODE == 1 ? 1u : 2u) * (kBigAStage + BSTAGE);
+    constexpr uint32_t IDESC_TF32 = PAIR ? kBigIdescPair : kBigIdesc, IDESC_BF16 = PAIR ? kBigIdescBf16Pair : kBigIdescBf16;
     // stage layout   MODE 1: [A 8K][B 16K]      MODE 3: [Ah 8K][Al 8K][Bh 16K][Bl 16K]
-    //                MODE 4: [Af 8K][Al bf16 4K][Ah bf16 4K][Bf 16K][Bh bf16 8K][Bl bf16 8K]
+    //                MODE 4: [Af 8K][Al bf16 4K][Ah bf16 4K][Bf 16K][Bh bf16 8K][Bl bf16 8K]        (PAIR: every B part is half as big)
     constexpr uint32_t OFF_B = (MODE == 1 ? 1u : 2u) * kBigAStage;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + kBigStages * STAGE);
-    uint64_t* empty = full + kBigStages;
-    uint64_t* accum = empty + kBigStages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NST * STAGE);
+    uint64_t* empty = full + NST;
+    uint64_t* accum = empty + NST;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;           // 0: leader (issues the MMAs of the pair)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slice = blockIdx.x, tile = blockIdx.y;
     const int KT = A.KG / kBigKS;
@@ -179,13 +235,15 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     // programmatic dependent launch: let the next step's grid start its prologue as soon as SMs free up ...
     if (!PERSIST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
-        for (int s = 0; s < kBigStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        // leader of a pair: a stage is full when its own copies have landed AND the peer has reported its copies
+        for (int s = 0; s < NST; ++s) { mbar_init(full + s, (PAIR && rank == 0) ? 2 : 1); mbar_init(empty + s, 1); }
         mbar_init(accum, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kBigTmemCols);
+    if (warp == 1) { if (PAIR) tmem_alloc_2(tmem_slot, kBigTmemCols); else tmem_alloc(tmem_slot, kBigTmemCols); }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) { cluster_arrive_release(); cluster_wait_acquire(); }      // the peer's barriers and TMEM are set up, too
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     const size_t plane = (size_t)A.tiles * A.KG * kTile;                 // float4 per FP32 plane of an A image
@@ -201,30 +259,31 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             const float4* Acur = big_step_of(A, it, PERSIST).Acur;
             const char* a0 = reinterpret_cast<const char*>(Acur + (size_t)tile * A.KG * kTile);
             const char* a1 = reinterpret_cast<const char*>(Acur + plane + (size_t)tile * A.KG * kTile);              // MODE 3: lo plane
-            const char* b0 = reinterpret_cast<const char*>(A.Bimg + (size_t)slice * A.KG * kBigNT);
-            const char* b1 = reinterpret_cast<const char*>(A.Bimg + planeB + (size_t)slice * A.KG * kBigNT);
+            const size_t blk = PAIR ? (size_t)slice * 2 + rank : (size_t)slice;          // B block: [slice] or [slice][half of the nodes]
+            const char* b0 = reinterpret_cast<const char*>(A.Bimg + blk * A.KG * BROWS);
+            const char* b1 = reinterpret_cast<const char*>(A.Bimg + planeB + blk * A.KG * BROWS);
             // MODE 4: bf16 planes, 16-byte rows of 8 nodes: [tile][KG/2][128] and [slice][KG/2][256] uint4
             const char* aL = reinterpret_cast<const char*>(Acur + plane) + (size_t)tile * (A.KG / 2) * kTile * 16;
             const char* aH = aL + plane * 8;
-            const char* bH = reinterpret_cast<const char*>(A.Bimg + planeB) + (size_t)slice * (A.KG / 2) * kBigNT * 16;
+            const char* bH = reinterpret_cast<const char*>(A.Bimg + planeB) + blk * (A.KG / 2) * BROWS * 16;
             const char* bL = bH + planeB * 8;
             const uint32_t base = smem_u32(smraw);
             for (int kt = 0; kt < KT; ++kt, ++ring) {
-                const int s = (int)(ring % kBigStages);
-                mbar_wait(empty + s, (uint32_t)(((ring / kBigStages) & 1) ^ 1));
+                const int s = (int)(ring % NST);
+                mbar_wait(empty + s, (uint32_t)(((ring / NST) & 1) ^ 1));
                 mbar_expect_tx(full + s, STAGE);
                 const uint32_t dst = base + (uint32_t)s * STAGE;
                 bulk_g2s(dst, a0 + (size_t)kt * kBigAStage, kBigAStage, full + s);
-                bulk_g2s(dst + OFF_B, b0 + (size_t)kt * kBigBStage, kBigBStage, full + s);
+                bulk_g2s(dst + OFF_B, b0 + (size_t)kt * BSTAGE, BSTAGE, full + s);
                 if (SPLIT) {
                     bulk_g2s(dst + kBigAStage, a1 + (size_t)kt * kBigAStage, kBigAStage, full + s);
-                    bulk_g2s(dst + OFF_B + kBigBStage, b1 + (size_t)kt * kBigBStage, kBigBStage, full + s);
+                    bulk_g2s(dst + OFF_B + BSTAGE, b1 + (size_t)kt * BSTAGE, BSTAGE, full + s);
                 }
                 if (MIXED) {
                     bulk_g2s(dst + kBigAStage, aL + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
                     bulk_g2s(dst + kBigAStage + kBigAStage / 2, aH + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
-                    bulk_g2s(dst + OFF_B + kBigBStage, bH + (size_t)kt * (kBigBStage / 2), kBigBStage / 2, full + s);
-                    bulk_g2s(dst + OFF_B + kBigBStage + kBigBStage / 2, bL + (size_t)kt * (kBigBStage / 2), kBigBStage / 2, full + s);
+                    bulk_g2s(dst + OFF_B + BSTAGE, bH + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
+                    bulk_g2s(dst + OFF_B + BSTAGE + BSTAGE / 2, bL + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
                 }
             }
         }
@@ -234,25 +293,36 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     } else if (warp == 1) {
       uint32_t ring = 0;
       for (int it = 0; it < nsteps; ++it) {
-        if (elect_one()) {
+        if (PAIR && rank != 0) {
+            // ---- peer of a CTA pair: no MMAs to issue; tell the leader when each of my stages has landed ----
+            if (elect_one()) {
+                for (int kt = 0; kt < KT; ++kt, ++ring) {
+                    const int s = (int)(ring % NST);
+                    mbar_wait(full + s, (uint32_t)((ring / NST) & 1));
+                    mbar_arrive_remote(full + s, 0);
+                }
+            }
+        } else if (elect_one()) {
             // ---- MMA issuer ----
             const uint32_t base = smem_u32(smraw);
             uint32_t acc = 0;
             tc_fence_after();                              // (persistent: the epilogue's TMEM reads of the previous step are done)
             for (int kt = 0; kt < KT; ++kt, ++ring) {
-                const int s = (int)(ring % kBigStages);
-                mbar_wait(full + s, (uint32_t)((ring / kBigStages) & 1));
+                const int s = (int)(ring % NST);
+                if (PAIR) mbar_wait_cluster(full + s, (uint32_t)((ring / NST) & 1));
+                else mbar_wait(full + s, (uint32_t)((ring / NST) & 1));
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)s * STAGE;
                 const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO);
-                const uint64_t bd_hi = umma_desc(sa + OFF_B, kBigLBO_B, kSBO), bd_lo = umma_desc(sa + OFF_B + kBigBStage, kBigLBO_B, kSBO);
+                const uint64_t bd_hi = umma_desc(sa + OFF_B, LBO_B, kSBO), bd_lo = umma_desc(sa + OFF_B + BSTAGE, LBO_B, kSBO);
 #pragma unroll
                 for (int k8 = 0; k8 < kBigKS / 2; ++k8) {
 #pragma unroll
                     for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
                         const uint64_t a0 = (pass == 1) ? ad_lo : ad_hi;
                         const uint64_t b0 = (pass == 2) ? bd_lo : bd_hi;
-                        umma_tf32(tmem_d, a0 + (uint64_t)(k8 * ((2 * kBigLBO_A) >> 4)), b0 + (uint64_t)(k8 * ((2 * kBigLBO_B) >> 4)), kBigIdesc, acc);
+                        const uint64_t ak = a0 + (uint64_t)(k8 * ((2 * kBigLBO_A) >> 4)), bk = b0 + (uint64_t)(k8 * ((2 * LBO_B) >> 4));
+                        if (PAIR) umma_tf32_2(tmem_d, ak, bk, IDESC_TF32, acc); else umma_tf32(tmem_d, ak, bk, IDESC_TF32, acc);
                         acc = 1;
                     }
                 }
@@ -260,16 +330,18 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                     // one K = 16 BF16 MMA per correction: the bf16 stage arrays are [2 eight-node groups][rows][16 B], i.e. the same
                     // core-matrix geometry (LBO = rows x 16 B, SBO = 128 B) as a K = 8 TF32 slice
                     const uint64_t aL = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO), aH = umma_desc(sa + kBigAStage + kBigAStage / 2, kBigLBO_A, kSBO);
-                    const uint64_t bH = umma_desc(sa + OFF_B + kBigBStage, kBigLBO_B, kSBO), bL = umma_desc(sa + OFF_B + kBigBStage + kBigBStage / 2, kBigLBO_B, kSBO);
+                    const uint64_t bH = umma_desc(sa + OFF_B + BSTAGE, LBO_B, kSBO), bL = umma_desc(sa + OFF_B + BSTAGE + BSTAGE / 2, LBO_B, kSBO);
 #pragma unroll
                     for (int k16 = 0; k16 < kBigKS / 4; ++k16) {
-                        umma_bf16(tmem_d, aL + (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), bH + (uint64_t)(k16 * ((2 * kBigLBO_B) >> 4)), kBigIdescBf16, 1);
-                        umma_bf16(tmem_d, aH + (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), bL + (uint64_t)(k16 * ((2 * kBigLBO_B) >> 4)), kBigIdescBf16, 1);
+                        const uint64_t da = (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), db = (uint64_t)(k16 * ((2 * LBO_B) >> 4));
+                        if (PAIR) { umma_bf16_2(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16_2(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
+                        else { umma_bf16(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
                     }
                 }
-                umma_commit(empty + s);        // the stage may be refilled once these MMAs have read it
+                // the stage may be refilled (in both CTAs of a pair) once these MMAs have read it
+                if (PAIR) umma_commit_2(empty + s); else umma_commit(empty + s);
             }
-            umma_commit(accum);
+            if (PAIR) umma_commit_2(accum); else umma_commit(accum);
         }
         __syncwarp();
         if (PERSIST) { cluster_arrive_release(); cluster_wait_acquire(); }
@@ -284,11 +356,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
         const int node_base = slice * kBigNT + cgp * kBigCols;
         const size_t rowbase = (size_t)tile * A.KG * kTile + r;
         const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
-        const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
+        const float sg0 = __fmul_rn(-1.4426950408889634f, A.par[2 * A.Bs + sim]), dsg = __fmul_rn(-1.4426950408889634f, A.par[3 * A.Bs + sim]);
         const uint64_t strm = A.streams[sim];
         const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
         const float Pmu = c.P - c.mu, nmu = -c.mu;
-        const float Gh = G0 + dG, sgh = sg0 + dsg;
+        const float Gh = __fadd_rn(G0, dG), sgh = __fadd_rn(sg0, dsg);
         int ng = (N - node_base + 7) / 8;
         ng = ng < 0 ? 0 : (ng > kBigCols / 8 ? kBigCols / 8 : ng);
 
@@ -318,7 +390,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 const size_t idx = idx0 + (size_t)qd * kTile;
                 uint32_t xp4[4];
                 float z[4];
-                normals4f(philox4x32_10(S.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
+                normals4f(philox4x32(S.step, (uint32_t)(node0 >> 2), s_lo, s_hi, c.k0, c.k1), z[0], z[1], z[2], z[3]);
                 float E[4] = {cur.eh.x, cur.eh.y, cur.eh.z, cur.eh.w};
                 if (!MIXED) { E[0] += cur.el.x; E[1] += cur.el.y; E[2] += cur.el.z; E[3] += cur.el.w; }
                 float I[4] = {cur.i.x, cur.i.y, cur.i.z, cur.i.w};
@@ -329,7 +401,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                     const int node = node0 + j;
                     const bool live = FULL || node < N;
                     if (S.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
-                    if (live && S.rec) A.Ebuf[((size_t)S.row * N + node) * A.Bs + sim] = E[j];      // state BEFORE the update (WC:129-130)
+                    if (live && S.rec && sim < A.Bo) A.Ebuf[((size_t)S.row * N + node) * A.Bo + sim] = E[j];      // state BEFORE the update (WC:129-130)
                     float xp = fmaf(c.sq, z[j], Pmu);
                     xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(c.a_ee, E[j], xp)));
                     xp4[j] = __float_as_uint(xp);
@@ -371,10 +443,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 }
                 const int node0 = node_base + 8 * g;
                 const size_t idx = rowbase + (size_t)(node0 >> 2) * kTile;
-                if (S.coup) {                    // test hook (first step only)
+                if (S.coup && sim < A.Bo) {      // test hook (first step only)
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (node0 + j < N) S.coup[(size_t)(node0 + j) * A.Bs + sim] = __uint_as_float(cr[j]);
+                        if (node0 + j < N) S.coup[(size_t)(node0 + j) * A.Bo + sim] = __uint_as_float(cr[j]);
                 }
                 float En[8];
 #pragma unroll
@@ -434,21 +506,25 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
       }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_d, kBigTmemCols);
+    if (PAIR) { cluster_arrive_release(); cluster_wait_acquire(); }      // neither CTA leaves while the pair's MMAs / arrivals may still touch it
+    else __syncthreads();
+    if (warp == 1) { if (PAIR) tmem_dealloc_2(tmem_d, kBigTmemCols); else tmem_dealloc(tmem_d, kBigTmemCols); }
 }
 
 // ---- staging ---------------------------------------------------------------------------------------------------------
 // SC (float64 [N][N], row = target node) -> B image hi/lo
-__global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, int mixed, float* Bimg) {
+// R = rows per block: 256 ([slice][KG][256][4]) or, for the CTA-pair kernel, 128 ([slice][half][KG][128][4])
+__global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, int mixed, int R, float* Bimg) {
     const size_t total = (size_t)slices * KG * kBigNT * 4;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int kk = (int)(idx & 3);
-    const int nl = (int)((idx >> 2) % kBigNT);
-    const size_t rest = (idx >> 2) / kBigNT;
-    const int kg = (int)(rest % KG), slice = (int)(rest / KG);
-    const int n = slice * kBigNT + nl, k = kg * 4 + kk;
+    const int row = (int)((idx >> 2) % R);
+    const size_t rest = (idx >> 2) / R;
+    const int kg = (int)(rest % KG);
+    const size_t blk = rest / KG;
+    const int per = kBigNT / R;
+    const int n = (int)(blk / per) * kBigNT + (int)(blk % per) * R + row, k = kg * 4 + kk;
     const float v = (n < N && k < N) ? (float)CM[(size_t)n * N + k] : 0.f;
     if (!mixed) {
         const float h = tf32_rn(v);
@@ -458,7 +534,7 @@ __global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, 
         Bimg[idx] = v;
         __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(Bimg + total);       // [slice][KG/2][256][8]
         __nv_bfloat16* L = H + total;
-        const size_t o = (((size_t)slice * (KG / 2) + (kg >> 1)) * kBigNT + nl) * 8 + (size_t)((kg & 1) * 4 + kk);
+        const size_t o = ((blk * (KG / 2) + (kg >> 1)) * R + row) * 8 + (size_t)((kg & 1) * 4 + kk);
         H[o] = __float2bfloat16_rn(v);
         L[o] = __float2bfloat16_rn(v - tf32_trunc(v));
     }
@@ -502,16 +578,17 @@ __global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, fl
 }
 
 // images -> final state [3][N][Bs] (E, I, a_ie), simulation fastest
-__global__ void big_export_kernel(int N, int KG, int64_t Bs, int mixed, const float* Aimg, size_t plane_f, const float* I, const float* ab,
+// (Bo = simulation stride of `fin`; the images may hold one more padding tile)
+__global__ void big_export_kernel(int N, int KG, int64_t Bo, int mixed, const float* Aimg, size_t plane_f, const float* I, const float* ab,
                                   const float* ad, float* fin) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= (int64_t)N * Bs) return;
-    const int64_t sim = k % Bs;
-    const int node = (int)(k / Bs);
+    if (k >= (int64_t)N * Bo) return;
+    const int64_t sim = k % Bo;
+    const int node = (int)(k / Bo);
     const size_t src = (((size_t)(sim / kTile) * KG + (node >> 2)) * kTile + (size_t)(sim % kTile)) * 4 + (node & 3);
     fin[k] = mixed ? Aimg[src] : Aimg[src] + Aimg[plane_f + src];
-    fin[(int64_t)N * Bs + k] = I[src];
-    fin[2 * (int64_t)N * Bs + k] = ab[src] + ad[src];
+    fin[(int64_t)N * Bo + k] = I[src];
+    fin[2 * (int64_t)N * Bo + k] = ab[src] + ad[src];
 }
 
 }  // namespace nrem

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(CM_SMEM ? 256 : 1024) wc_run_f64_kernel(const 
                 if (nz_base) {
                     nz = nz_base[(size_t)step * N + i];
                 } else {
-                    const Philox4 r = philox4x32_10((uint32_t)step, (uint32_t)(i >> 2), (uint32_t)strm, (uint32_t)(strm >> 32), k0, k1);
+                    const Philox4 r = philox4x32((uint32_t)step, (uint32_t)(i >> 2), (uint32_t)strm, (uint32_t)(strm >> 32), k0, k1);
                     const bool second = (i & 2) != 0;
                     const double rad = sqrt(-2.0 * log(u23d(second ? r.z : r.x)));
                     const double ang = 6.283185307179586476925286766559 * (u23d(second ? r.w : r.y) - 0.5);

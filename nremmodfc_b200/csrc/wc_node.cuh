@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kNodeThreads, 1) wc_node_kernel(const BatchArg
                 }
             } else { E[j] = 0.f; I[j] = 0.f; ab[j] = 0.f; ad[j] = 0.f; }
             const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
-            const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
+            const float sg0 = __fmul_rn(-1.4426950408889634f, A.par[2 * A.Bs + sim]), dsg = __fmul_rn(-1.4426950408889634f, A.par[3 * A.Bs + sim]);
             Gi[j] = fmaf(dG, mGn, G0);                  // homogeneous maps: fmaf(dG, 1, G0) == G0 + dG, the scalar of wc_tc.cuh's HOMO kernel
             sg2[j] = fmaf(dsg, mSn, sg0);
         }
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kNodeThreads, 1) wc_node_kernel(const BatchArg
             }
 #pragma unroll
             for (int cc = 0; cc < SPT / 4; ++cc) {
-                const Philox4 ph = philox4x32_10(step, quad, s_lo[cc], s_hi[cc], c.k0, c.k1);
+                const Philox4 ph = philox4x32(step, quad, s_lo[cc], s_hi[cc], c.k0, c.k1);
                 const float l0 = lg2f(u23f(ph.x)), l1 = lg2f(u23f(ph.z));
                 const float a0r = fmaf(__uint_as_float(0x3f800000u | (ph.y >> 9)), two_pi, -1.49999994f * two_pi);
                 const float a1r = fmaf(__uint_as_float(0x3f800000u | (ph.w >> 9)), two_pi, -1.49999994f * two_pi);

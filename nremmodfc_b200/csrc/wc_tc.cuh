@@ -240,7 +240,9 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
         }
     }
     const float G0 = A.par[sim], dG = A.par[A.Bs + sim];
-    const float sg0 = -1.4426950408889634f * A.par[2 * A.Bs + sim], dsg = -1.4426950408889634f * A.par[3 * A.Bs + sim];
+    // (explicit roundings: with -fmad the compiler would otherwise contract sg0 + dsg into an FMA of the unrounded product, and the
+    // homogeneous kernel would differ in the last bit from fmaf(dsg, 1, sg0) of the map kernels / wc_node.cuh)
+    const float sg0 = __fmul_rn(-1.4426950408889634f, A.par[2 * A.Bs + sim]), dsg = __fmul_rn(-1.4426950408889634f, A.par[3 * A.Bs + sim]);
     const uint64_t strm = A.streams[sim];
     const uint32_t s_lo = (uint32_t)strm, s_hi = (uint32_t)(strm >> 32);
     if (MAPS_TMEM) {
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     float4* Al4 = reinterpret_cast<float4*>(Al);
     const float Pmu = c.P - c.mu;                        // constant part of the E sigmoid argument
     const float nmu = -c.mu, nkr = -A.kA * c.rhoE;
-    const float Gh = G0 + dG, sgh = sg0 + dsg;           // HOMO: map == 1 everywhere
+    const float Gh = __fadd_rn(G0, dG), sgh = __fadd_rn(sg0, dsg);     // HOMO: map == 1 everywhere (== fmaf(dG, 1, G0), fmaf(dsg, 1, sg0))
     const float two_pi = 6.2831853071795865f, m2ln2 = -1.3862943611198906f;
 
     // The step loop for a chunk with KN live nodes (KN = CH, or 18 for the last chunk of N = 90).
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
                 a[k] = fmaf(I[k], fmaf(E[k], A.kA, nkr), a[k]);
                 I[k] = fmaf(c.kI, fmaf(fmaf(-c.rI, I[k], 1.0f), SI, -I[k]), I[k]);
             };
-            Philox4 ph = philox4x32_10(step, (uint32_t)(chunk * (CH / 4)), s_lo, s_hi, c.k0, c.k1);
+            Philox4 ph = philox4x32(step, (uint32_t)(chunk * (CH / 4)), s_lo, s_hi, c.k0, c.k1);
 #pragma unroll
             for (int g = 0; g < NQ; ++g) {
                 const float l0 = lg2f(u23f(ph.x)), l1 = lg2f(u23f(ph.z));
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
                     // PIPE != 0: A.zero is 0 at run time but opaque to ptxas, so the next quad's counter truly depends on a
                     // MUFU result of this quad (one LOP3 per quad) and its Philox rounds cannot be hoisted in front of it
                     const uint32_t ctr = PIPE == 0 ? step : (step ^ (__float_as_uint(PIPE == 1 ? l0 : z0) & A.zero));
-                    ph = philox4x32_10(ctr, (uint32_t)(chunk * (CH / 4) + g + 1), s_lo, s_hi, c.k0, c.k1);
+                    ph = philox4x32(ctr, (uint32_t)(chunk * (CH / 4) + g + 1), s_lo, s_hi, c.k0, c.k1);
                 }
                 xp[4 * g + 0] = fmaf(c.sq, z0, Pmu);
                 xp[4 * g + 1] = fmaf(c.sq, r0 * sinaf(a0), Pmu);

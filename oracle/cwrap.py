@@ -36,8 +36,8 @@ def lib():
         L.orc_bold_sim.argtypes = [dp, C.c_int64, C.c_int, C.c_double, dp]
         L.orc_philox_normals.restype = None
         L.orc_philox_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, dp]
-        L.orc_philox4x32_10.restype = None
-        L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.orc_philox4x32.restype = None
+        L.orc_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
 

@@ -1,4 +1,4 @@
-"""Philox4x32-10 + Box-Muller noise stream "nrem-philox-v1" (numpy reference).
+"""Philox4x32-7 + Box-Muller noise stream "nrem-philox-v2" (numpy reference).
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
@@ -6,8 +6,11 @@ The reference draws its noise from numba's MT19937 stream, which it never
 seeds (SURVEY.md "established by running" item 3): a "seed" there is only a
 replicate label.  The B200 path therefore defines its own counter-based stream
 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11 —
-Philox4x32 with 10 rounds) and this file restates it on the CPU so the CUDA
-generator can be checked bit-for-bit (integers) and to 1 ulp-ish (normals).
+Philox4x32 with ROUNDS = 7 rounds, the smallest count that passes BigCrush in
+that paper; stream v1 of round 1 used the library default of 10) and this file
+restates it on the CPU so the CUDA generator can be checked bit-for-bit
+(integers, incl. Random123's known-answer vectors for 7 and 10 rounds) and to
+1 ulp-ish (normals).
 
 Stream definition
 -----------------
@@ -31,14 +34,15 @@ M1 = np.uint64(0xCD9E8D57)
 W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
+ROUNDS = 7            # == NREM_PHILOX_ROUNDS of nremmodfc_b200/csrc/philox.cuh
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10.  All arguments broadcastable uint32 arrays."""
+def philox4x32(c0, c1, c2, c3, k0, k1, rounds=ROUNDS):
+    """Vectorised Philox4x32-<rounds>.  All arguments broadcastable uint32 arrays."""
     c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint64) & MASK for c in np.broadcast_arrays(c0, c1, c2, c3)]
     k0 = int(k0) & 0xFFFFFFFF
     k1 = int(k1) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = M0 * c0
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
@@ -66,7 +70,7 @@ def normals(seed, stream, step, nnodes):
     stream, step = np.broadcast_arrays(stream, step)
     nq = (nnodes + 3) // 4
     q = np.arange(nq, dtype=np.uint64)
-    x0, x1, x2, x3 = philox4x32_10(step[..., None], q, (stream & MASK)[..., None], (stream >> np.uint64(32))[..., None],
+    x0, x1, x2, x3 = philox4x32(step[..., None], q, (stream & MASK)[..., None], (stream >> np.uint64(32))[..., None],
                                    seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     r0 = np.sqrt(-2.0 * np.log(uniform23(x0)))
     r1 = np.sqrt(-2.0 * np.log(uniform23(x2)))

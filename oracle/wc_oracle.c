@@ -9,7 +9,7 @@
  *              i % downsamp == 0 in phase 3.
  * orc_bold_sim follows the Balloon-Windkessel restatement of oracle/bold_oracle.py
  *              (BOLDModel.Sim, call site netwWilsonCowanPlastic.py:144; parity unpinned).
- * orc_philox_normals  the "nrem-philox-v1" stream of oracle/philox.py.
+ * orc_philox_normals  the "nrem-philox-v2" stream of oracle/philox.py (Philox4x32-7).
  *
  * Build: make -C oracle   (gcc -O2 -fno-fast-math; scalar, one thread)
  */
@@ -38,10 +38,12 @@ static inline void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1) {
     c[2] = n2;
 }
 
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+#define ORC_PHILOX_ROUNDS 7       /* the stream definition (oracle/philox.py ROUNDS) */
+
+void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         philox_round(c, k0, k1);
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
@@ -60,7 +62,7 @@ void orc_philox_normals(uint64_t seed, uint64_t stream, uint32_t step, int N, do
         uint32_t ctr[4] = {step, (uint32_t)q, (uint32_t)stream, (uint32_t)(stream >> 32)};
         uint32_t x[4];
         double v[4];
-        orc_philox4x32_10(ctr, key, x);
+        orc_philox4x32(ctr, key, ORC_PHILOX_ROUNDS, x);
         double r0 = sqrt(-2.0 * log(u23(x[0]))), a0 = two_pi * (u23(x[1]) - 0.5);
         double r1 = sqrt(-2.0 * log(u23(x[2]))), a1 = two_pi * (u23(x[3]) - 0.5);
         v[0] = r0 * cos(a0); v[1] = r0 * sin(a0);

@@ -404,7 +404,7 @@ def test_sweep_with_more_tiles_than_sms(aal90):
     rng = np.random.default_rng(5)
     dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
     streams = rng.integers(0, 2 ** 60, B).astype(np.uint64)
-    kw = dict(Neq=40, bold_downsamp=5, chunk_samples=50, bold_f32=True)
+    kw = dict(Neq=40, bold_downsamp=5, chunk_samples=50, bold_f32=True, kernel="tc3")   # (auto would give the small batch 16-simulation tiles)
     plan = sweep.SweepPlan(p, B, **kw)
     plan.set_profiling(True)
     big = plan.run(aal90["SC"], emp, np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams)
@@ -640,6 +640,28 @@ def test_large_connectome_persistent_cluster_mode_is_bit_identical(monkeypatch):
     monkeypatch.setenv("NREM_BIG_PERSIST", "1")
     E1, f1 = ops.big_integrate_f32(*args, **kw)
     assert E0.shape == (4, N, B) and np.isfinite(f0).all()
+    assert np.array_equal(E0, E1) and np.array_equal(f0, f1)
+
+
+@pytest.mark.parametrize("kernel,B", [("tcb", 1100), ("tc3", 256), ("tc", 384)])
+def test_large_connectome_cta_pair_mode_is_bit_identical(kernel, B, monkeypatch):
+    """CTA pairs (tcgen05 cta_group::2: two 128-simulation tiles per M = 256 MMA, each CTA staging half of the SC tile) against
+    single-CTA MMAs: same products, same accumulation order, so E samples, final state and the first coupling must be identical
+    bit for bit.  B = 1100 is 9 tiles (padded to 10 for the pairs), B = 384 is 3 tiles (pairs forced, padded to 4)."""
+    from nremmodfc_b200 import ops
+    N = 520
+    SC = _random_sc(N, 4)
+    rng = np.random.default_rng(9)
+    p = ops.make_params(N, 30, 100, 80, P=0.4, rhoE=0.18, seed=6)
+    args = (p, SC, np.full(B, 0.16), rng.uniform(-0.1, 0.3, B), np.full(B, 7.68), rng.uniform(-0.2, 0.2, B))
+    kw = dict(mapG=rng.uniform(0.5, 1.5, N), mapS=rng.uniform(0.8, 1.2, N), streams=rng.integers(0, 2 ** 62, B).astype(np.uint64),
+              kernel=kernel, want_coupling=True)
+    monkeypatch.setenv("NREM_BIG_PAIR", "0")
+    E0, f0, c0 = ops.big_integrate_f32(*args, **kw)
+    monkeypatch.setenv("NREM_BIG_PAIR", "1")
+    E1, f1, c1 = ops.big_integrate_f32(*args, **kw)
+    assert E0.shape == (4, N, B) and np.isfinite(f0).all() and np.isfinite(f1).all()
+    assert np.array_equal(c0, c1), float(np.max(np.abs(c0 - c1)))
     assert np.array_equal(E0, E1) and np.array_equal(f0, f1)
 
 

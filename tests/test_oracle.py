@@ -56,14 +56,18 @@ def test_bold_c_equals_numpy(oracle_lib):
 
 
 def test_philox_kat_and_c_equals_numpy(oracle_lib):
-    # Random123 known-answer vectors for philox4x32-10
-    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
-           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
-           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
-            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
-    for ctr, key, exp in kat:
-        out = philox.philox4x32_10(*[np.uint32(c) for c in ctr], *key)
-        assert tuple(int(o) for o in out) == exp
+    # Random123 known-answer vectors (kat_vectors) for philox4x32 with 10 rounds and with 7, the stream's round count
+    ctrs = [((0, 0, 0, 0), (0, 0)), ((0xffffffff,) * 4, (0xffffffff,) * 2),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0))]
+    kat = {10: [(0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd),
+                (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)],
+           7: [(0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48), (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662),
+               (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a)]}
+    assert philox.ROUNDS == 7
+    for rounds, exps in kat.items():
+        for (ctr, key), exp in zip(ctrs, exps):
+            out = philox.philox4x32(*[np.uint32(c) for c in ctr], *key, rounds=rounds)
+            assert tuple(int(o) for o in out) == exp
     z = philox.normals(12345, np.array([7, 8], dtype=np.uint64), 99, 90)
     assert np.array_equal(z[1], oracle_lib.philox_normals(12345, 8, 99, 90))
     zz = philox.normals(1, np.arange(100, dtype=np.uint64)[:, None], np.arange(300, dtype=np.uint64)[None, :], 90)
