@@ -475,9 +475,11 @@ def run_ours(args):
             roof["traffic_note"] = "dram read+write bytes of one recording launch (ncu --set full), scaled to the tiles of one launch; " + lim["source"]
             roof["composite"] = {"floors_clk_per_tile_step": floors, "binding": binding, "measured_clk_per_tile_step": clk_per_tile_step,
                                  "frac": floors[binding] / clk_per_tile_step, "pipe_busy_pct_ncu": lim["pipe_busy_pct"],
-                                 "definition": "floor = cycles one SM needs for one Euler step of a 128-simulation tile if that resource alone were "
-                                               "the limit (XU: MUFU lane-ops / 16 per clk; issue: warp instructions / 4 schedulers; tensor: 36 MMAs x "
-                                               "48 clk; FMA: FFMA-pipe warp instructions / 4 x 2 clk), counted from the SASS / ncu capture of this kernel",
+                                 "definition": "floor = SM cycles one Euler step of a 128-simulation tile would need if that resource alone were the "
+                                               "limit = its busy fraction in the committed ncu capture of this kernel x the capture's cycles per step "
+                                               "(cross-check from the SASS: XU = MUFU lane-ops / 16 per clk, issue = warp instructions / 4 schedulers, "
+                                               "tensor = 36 MMAs x 48 clk); measured = device time of the live run x SM clock x busy SMs / tile-steps, "
+                                               "i.e. it also carries the BOLD/filter launches and the tile-group scheduling of the sweep",
                                  "source": lim["source"]}
         else:
             roof["traffic"] = None

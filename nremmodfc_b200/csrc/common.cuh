@@ -20,7 +20,10 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
 #define NREM_CUDA(call)                                                                     \
     do {                                                                                    \
         cudaError_t e_ = (call);                                                            \
-        if (e_ != cudaSuccess) return nrem::fail(NREM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+        if (e_ != cudaSuccess) {                                                            \
+            cudaGetLastError();      /* reset the per-thread error so that the next call does not report this one again */ \
+            return nrem::fail(NREM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+        }                                                                                   \
     } while (0)
 
 #define NREM_REQUIRE(cond, msg)                                          \

@@ -1005,6 +1005,15 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
         A.Bs = Bs; A.Bo = round_up(B, kTile); A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
         A.Ebuf = E_samples;
+        // NREM_BIG_DBG=<step>: phase timing of that Euler step (globaltimer stamps per CTA, printed to stderr) -- developer switch
+        const char* env_dbg = getenv("NREM_BIG_DBG");
+        const int64_t dbg_step = env_dbg ? atoll(env_dbg) : -1;
+        unsigned long long* dbg_dev = nullptr;
+        A.dbg = nullptr;
+        if (dbg_step >= 0) {
+            NREM_CUDA(cudaMalloc((void**)&dbg_dev, sizeof(unsigned long long) * 8 * (size_t)slices * tiles * 2));
+            NREM_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(unsigned long long) * 8 * (size_t)slices * tiles * 2, st));
+        }
         const bool fullN = N % 8 == 0, homoN = A.homo != 0;
         // variant: 0 = one launch per step, 1 = persistent cluster, 2 = one launch per step with CTA pairs
         auto pick = [&](auto mode, auto variant) -> void (*)(const BigArgs) {
@@ -1018,9 +1027,10 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
                  : k == 3 ? pick(std::integral_constant<int, 3>{}, variant) : pick(std::integral_constant<int, 1>{}, variant);
         };
         const int smem = pair ? (k == 2 ? big_smem_bytes<1, true>() : big_smem_bytes<3, true>()) : (k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>());
-        const dim3 grid((unsigned)slices, (unsigned)tiles);
+        const dim3 grid = pair ? dim3((unsigned)tiles, (unsigned)slices) : dim3((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
-        static const bool pdl = []() { const char* e = getenv("NREM_BIG_PDL"); return e ? atoi(e) != 0 : true; }();
+        const char* env_pdl = getenv("NREM_BIG_PDL");
+        const bool pdl = env_pdl ? atoi(env_pdl) != 0 : true;
         A.img[0] = img[0]; A.img[1] = img[1];
         A.n1 = (uint32_t)p->n1; A.n12 = (uint32_t)(p->n1 + p->n2); A.downsamp = p->downsamp;
         for (int ph = 0; ph < 3; ++ph) A.kA3[ph] = (float)(p->dtSim / p->tau_ip[ph]);
@@ -1061,6 +1071,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
                 A.rec = (E_samples && ph == 2 && it % p->downsamp == 0) ? 1 : 0;
                 A.row = A.rec ? it / p->downsamp : 0;
                 A.coup = s == 0 ? coup_first : nullptr;
+                A.dbg = (dbg_dev && (s == dbg_step || s == dbg_step + 1)) ? dbg_dev + (s - dbg_step) * 8 * (size_t)slices * tiles : nullptr;
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
                 cfg.dynamicSmemBytes = (size_t)smem;
@@ -1068,7 +1079,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
                 int na = 0;
                 if (pair) {       // tiles 2p, 2p+1 of a node slice = one cluster = one CTA pair
                     at[na].id = cudaLaunchAttributeClusterDimension;
-                    at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 2; at[na].val.clusterDim.z = 1;
+                    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
                     ++na;
                 }
                 if (pdl) {
@@ -1082,6 +1093,27 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             }
         }
         NREM_CUDA(cudaEventRecord(t1, st));
+        if (dbg_dev) {
+            const size_t nc = (size_t)slices * tiles;
+            std::vector<unsigned long long> h(16 * nc);
+            NREM_CUDA(cudaMemcpyAsync(h.data(), dbg_dev, sizeof(unsigned long long) * 16 * nc, cudaMemcpyDeviceToHost, st));
+            NREM_CUDA(cudaStreamSynchronize(st));
+            cudaFree(dbg_dev);
+            unsigned long long t0min = ~0ull, t0next = ~0ull;
+            for (size_t c = 0; c < nc; ++c) { if (h[c * 8 + 1]) t0min = std::min(t0min, h[c * 8 + 1]); if (h[(nc + c) * 8 + 1]) t0next = std::min(t0next, h[(nc + c) * 8 + 1]); }
+            const char* names[7] = {"CTA start", "dependency wait over", "last MMA issued", "phase 1 done", "accumulator ready", "phase 2 done (first warp)", "phase 2 done (last warp)"};
+            fprintf(stderr, "[NREM_BIG_DBG] step %lld, %zu CTAs; microseconds after the earliest 'dependency wait over' (min / mean / max over CTAs)\n", (long long)dbg_step, nc);
+            for (int k = 0; k < 7; ++k) {
+                double mn = 1e30, mx = -1e30, sum = 0; size_t cnt = 0;
+                for (size_t c = 0; c < nc; ++c) {
+                    if (!h[c * 8 + k]) continue;
+                    const double v = ((double)h[c * 8 + k] - (double)t0min) * 1e-3;
+                    mn = std::min(mn, v); mx = std::max(mx, v); sum += v; ++cnt;
+                }
+                if (cnt) fprintf(stderr, "[NREM_BIG_DBG]   %-28s %8.2f %8.2f %8.2f  (%zu)\n", names[k], mn, sum / cnt, mx, cnt);
+            }
+            fprintf(stderr, "[NREM_BIG_DBG]   next step's earliest 'dependency wait over': %8.2f\n", ((double)t0next - (double)t0min) * 1e-3);
+        }
         const int64_t n = (int64_t)N * A.Bo;
         big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, A.Bo, mixed, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
                                                                       (const float*)A.ab4, (const float*)A.ad4, final_state);

@@ -49,9 +49,12 @@ constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(
 
 // PAIR (cta_group::2): two CTAs of a cluster (two 128-simulation tiles, same node slice) execute ONE M = 256 MMA per K slice; each
 // CTA stages its own A tile and only HALF of the B tile (128 of the 256 output nodes), the tensor cores of the pair exchange the
-// halves.  Per SM and 16 input nodes that is 32 KB instead of 48 KB through the bulk-copy ring and shared memory, which buys a
-// 6-stage ring in the same shared memory.
-constexpr int kBigStagesPair = 6;
+// halves.  Per SM and 16 input nodes that is 32 KB instead of 48 KB through the bulk-copy ring and shared memory, which buys 
+// 7-stage ring in the same shared memory.
+#ifndef NREM_BIG_STAGES_PAIR
+#define NREM_BIG_STAGES_PAIR 7
+#endif
+constexpr int kBigStagesPair = NREM_BIG_STAGES_PAIR;
 template <int MODE, bool PAIR = false>
 constexpr uint32_t big_stage_bytes() { return (MODE == 1 ? 1u : 2u) * (kBigAStage + (PAIR ? kBigBStage / 2 : kBigBStage)); }
 template <int MODE, bool PAIR = false>
@@ -87,21 +90,17 @@ __device__ __forceinline__ void tmem_dealloc_2(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-// arrive (release at cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+// Arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  RELAXED: the arriving thread publishes no
+// data of its own — the stage was written into this CTA's shared memory by the bulk-copy engine (whose completion this thread has
+// observed on the local mbarrier) and is read in place by the pair's tensor cores, like a cta_group::2 TMA that signals the leader's
+// barrier directly.  (A .release.cluster arrive compiles to MEMBAR.ALL.GPU per stage and made the step 60 % slower.)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok, spins = 0;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 26)) __trap();
-    } while (!ok);
-}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ uint32_t bf16x2(float lo_elem, float hi_elem) {       // {lo_elem in bits 0..15, hi_elem in 16..31}, RN
@@ -118,7 +117,7 @@ struct BigArgs {
     float4* I4;
     float4* ab4;               // a_ie base
     float4* ad4;               // a_ie delta (a_ie = base + delta, see wc_tc.cuh)
-    const float* par;          // [4][Bs]: G0, dG, sigma0, dsigma
+    const float* par;          // [4][Bs]: G0, dG, sigma0, dsigm
     const uint64_t* streams;   // [Bs]
     const float* mapG;         // [4*KG]
     const float* mapS;
@@ -140,7 +139,11 @@ struct BigArgs {
     float kA3[3];              // dtSim / tau_ip per phase
     int downsamp;
     float4* img[2];            // the two A images; E(t) of global step s is img[s & 1]
+    unsigned long long* dbg;   // NULL, or [CTAs][8] %globaltimer stamps of this launch (NREM_BIG_DBG: phase timing of one step)
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define NREM_BIG_STAMP(slot) do { if (A.dbg && lane == 0) A.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = gtime_ns(); } while (0)
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
@@ -202,7 +205,7 @@ struct BigQuad {             // state of one thread's four-node group
 // FULL: N is a multiple of 8, so no node of a processed 8-node group is padding.  HOMO: no per-node maps (G, sigma per simulation)
 // PERSIST: launched as thread-block clusters of `slices` CTAs (the node slices of one 128-simulation tile, which depend only on each
 //          other); the cluster runs A.nsteps Euler steps with one barrier.cluster per step instead of one launch per step.
-// PAIR   : launched as clusters (1, 2, 1): tiles 2p and 2p+1 of a node slice form a CTA pair (cta_group::2).  Rank 0 issues the
+// PAIR   : launched as clusters (2, 1, 1) on a (tiles, slices) grid: tiles 2p and 2p+1 of a node slice form a CTA pair (cta_group::2).  Rank 0 issues the
 //          M = 256 MMAs for both; every CTA streams its own A tile and its half of the B tile; the peer relays "my stage has
 //          landed" to the leader's full barrier; tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both.
 template <int MODE, bool FULL, bool HOMO, bool PERSIST, bool PAIR = false>
@@ -226,12 +229,14 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;           // 0: leader (issues the MMAs of the pair)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int slice = blockIdx.x, tile = blockIdx.y;
+    // grid (slices, tiles); the CTA-pair kernel is launched as (tiles, slices) with clusters (2, 1, 1) = tiles 2p, 2p+1 of a slice
+    const int slice = PAIR ? blockIdx.y : blockIdx.x, tile = PAIR ? blockIdx.x : blockIdx.y;
     const int KT = A.KG / kBigKS;
     const BatchConst& c = A.c;
     const int N = c.N;
 
     const int nsteps = PERSIST ? A.nsteps : 1;
+    if (warp == 2) NREM_BIG_STAMP(0);                    // CTA start
     // programmatic dependent launch: let the next step's grid start its prologue as soon as SMs free up ...
     if (!PERSIST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     }
     if (warp == 1) { if (PAIR) tmem_alloc_2(tmem_slot, kBigTmemCols); else tmem_alloc(tmem_slot, kBigTmemCols); }
     tc_fence_before();
-    if (PAIR) { cluster_arrive_release(); cluster_wait_acquire(); }      // the peer's barriers and TMEM are set up, too
+    if (PAIR) { cluster_arrive_relaxed(); cluster_wait(); }      // the peer's barriers (fence.mbarrier_init above) and TMEM are set up, too
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     const size_t planeB = (size_t)A.slices * A.KG * kBigNT;              // float4 per FP32 plane of the B image
     // ... and wait here until the previous step's grid has completed and its E(t), I, a_ie are visible
     if (!PERSIST) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (warp == 2) NREM_BIG_STAMP(1);                    // previous step complete and visible
 
     if (warp == 0) {
       uint32_t ring = 0;                                  // stages issued so far (continues across the steps of a persistent launch)
@@ -309,8 +315,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             tc_fence_after();                              // (persistent: the epilogue's TMEM reads of the previous step are done)
             for (int kt = 0; kt < KT; ++kt, ++ring) {
                 const int s = (int)(ring % NST);
-                if (PAIR) mbar_wait_cluster(full + s, (uint32_t)((ring / NST) & 1));
-                else mbar_wait(full + s, (uint32_t)((ring / NST) & 1));
+                mbar_wait(full + s, (uint32_t)((ring / NST) & 1));
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)s * STAGE;
                 const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO);
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 if (PAIR) umma_commit_2(empty + s); else umma_commit(empty + s);
             }
             if (PAIR) umma_commit_2(accum); else umma_commit(accum);
+            NREM_BIG_STAMP(2);                           // last MMA issued
         }
         __syncwarp();
         if (PERSIST) { cluster_arrive_release(); cluster_wait_acquire(); }
@@ -420,10 +426,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             }
             tmem_st_wait();
         }
+        if (warp == 2) NREM_BIG_STAMP(3);                // phase 1 done (warp 2)
         // -- phase 2, after the last MMA: x = xp + G coup -> E(t+1), stored as the next A image
         {
             constexpr int NE = MIXED ? 2 : 4;
-            float4 ce[NE], ne[NE];               // MODE 1/3: eh[0], eh[1], el[0], el[1];  MODE 4: E[0], E[1]
+            float4 ce[NE], ne[NE], n2[NE];       // MODE 1/3: eh[0], eh[1], el[0], el[1];  MODE 4: E[0], E[1]
+            constexpr bool AHEAD2 = MIXED;       // E(t) of group g + 2 requested while group g is computed (8 registers in MODE 4): an L2
+                                                 // round trip is longer than one group's arithmetic
             auto loadE = [&](int g, float4 (&e)[NE]) {
                 const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
                 e[0] = S.Acur[idx]; e[1] = S.Acur[idx + kTile];
@@ -432,12 +441,15 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             // software pipeline: the TMEM loads (coupling + xp) and the E(t) loads of group g + 1 are in flight while group g is computed
             uint32_t cr[8], xp8[8], crn[8], xpn[8];
             if (ng > 0) { loadE(0, ce); tmem_ld8(tmem_mine + kBigNT, xp8); }          // xp does not depend on the MMAs
+            if (AHEAD2 && ng > 1) loadE(1, ne);
             mbar_wait(accum, (uint32_t)(it & 1));
             tc_fence_after();
+            if (warp == 2) NREM_BIG_STAMP(4);            // accumulator complete
             if (ng > 0) { tmem_ld8(tmem_mine, cr); tmem_ld_wait16(cr, xp8); }
             for (int g = 0; g < ng; ++g) {
                 if (g + 1 < ng) {
-                    loadE(g + 1, ne);
+                    if (!AHEAD2) loadE(g + 1, ne);
+                    else if (g + 2 < ng) loadE(g + 2, n2);
                     tmem_ld8(tmem_mine + 8 * (g + 1), crn);
                     tmem_ld8(tmem_mine + kBigNT + 8 * (g + 1), xpn);
                 }
@@ -489,11 +501,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 }
                 if (g + 1 < ng) tmem_ld_wait16(crn, xpn);
 #pragma unroll
-                for (int k = 0; k < NE; ++k) ce[k] = ne[k];
+                for (int k = 0; k < NE; ++k) { ce[k] = ne[k]; if (AHEAD2) ne[k] = n2[k]; }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { cr[k] = crn[k]; xp8[k] = xpn[k]; }
             }
         }
+            if (warp == 2) NREM_BIG_STAMP(5);            // phase 2 done (warp 2)
+            if (warp == 17) NREM_BIG_STAMP(6);           // phase 2 done (last epilogue warp)
             if (PERSIST) {
             // E(t+1), I, a_ie of this CTA's node slice are written: make them visible to the other slices' bulk copies (async proxy) ...
             if (A.nsteps < 0) __threadfence();       // (never: barrier.cluster release/acquire already orders the stores at cluster scope)
@@ -506,7 +520,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
       }
     }
     tc_fence_before();
-    if (PAIR) { cluster_arrive_release(); cluster_wait_acquire(); }      // neither CTA leaves while the pair's MMAs / arrivals may still touch it
+    if (PAIR) { cluster_arrive_relaxed(); cluster_wait(); }      // neither CTA leaves while the pair's MMAs / arrivals may still touch it (no data ordered)
     else __syncthreads();
     if (warp == 1) { if (PAIR) tmem_dealloc_2(tmem_d, kBigTmemCols); else tmem_dealloc(tmem_d, kBigTmemCols); }
 }
