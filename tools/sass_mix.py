@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "nremmodfc_b200", "csrc", "libnremfc.so")
+LIB = os.environ.get("NREM_LIB_PATH") or os.path.join(ROOT, "nremmodfc_b200", "csrc", "libnremfc.so")
 KERNEL = sys.argv[1] if len(sys.argv) > 1 else "wc_batch_tc_kernelILi3ELi24ELb1ELb1ELi0EE"
 
 CLASSES = [
