@@ -280,6 +280,31 @@ def config5_leg(N=1000, B=4096, steps=40000):
                          "kernel": "wc_big_step_kernel<4>", "profile": "profiles/r01_big_connectome.md"}}
 
 
+def config1_leg(d, SC, emp):
+    """BASELINE configs[0]: ONE full-length run (AAL90, G = 0.16, sigma = 7.68, one seed) through the drop-in module surface, exactly the
+    reference's call sequence (cortex_run.py:103-116 / whole_sweep_both.py:66-96): attributes, run.recompile(), run() -> Y_t float64
+    [300000, 3, 90], simBOLD(), np.corrcoef, utils.get_all_metrics vs mean_mat_W.  Float64 one-CTA kernel: the time loop of a single simulation
+    is sequential, so this is a latency figure (us per Euler step), not a throughput one."""
+    from nremmodfc_b200 import netwWilsonCowanPlastic as wc, utils
+    wc.P, wc.rhoE, wc.CM = 0.4, 0.18, SC
+    wc.tTrans1, wc.tTrans2, wc.tstop = 1, 400, 600
+    wc.timeTrans1, wc.timeTrans2 = np.arange(0, 1, wc.dtSim), np.arange(0, 400, wc.dtSim)
+    wc.timeSim, wc.time = np.arange(0, 600, wc.dtSim), np.arange(0, 600, wc.dt)
+    wc.G, wc.sigmaE, wc.sid = 0.16, 7.68, 0
+    t0 = time.perf_counter()
+    wc.run.recompile()
+    tray = wc.run()
+    t1 = time.perf_counter()
+    BOLD = wc.simBOLD(tray[:, 0, :], nnodes=90)
+    sFC = np.corrcoef(BOLD.T)
+    m = utils.get_all_metrics(sFC, emp[0], data_range=1)
+    t2 = time.perf_counter()
+    return {"workload": "configs[0]: one Wilson-Cowan + BOLD run, AAL90, G=0.16, sigma=7.68, 1+400+600 s, FC + GoF vs mean_mat_W, through "
+                        "netwWilsonCowanPlastic.run() / simBOLD() (float64, Y_t of 648 MB returned to the host)",
+            "run_s": t1 - t0, "us_per_euler_step": (t1 - t0) / STEPS_PER_SIM * 1e6, "bold_fc_gof_s": t2 - t1, "total_s": t2 - t0,
+            "corrW": float(m[0]), "eW": float(m[1]), "ssimW": float(m[2]), "results_finite": bool(np.isfinite(sFC).all())}
+
+
 def modality_leg(args, d, SC, emp, which):
     """BASELINE configs[2] / configs[3]: one whole 20 000-simulation sweep with heterogeneous NA/ACh maps (whole_sweep_both_maps.py:
     104-108), full length, through the same host API; sims/s from the wall clock of the call (H2D and D2H included)."""
@@ -513,6 +538,8 @@ def run_ours(args):
                 line["modalities"] = [modality_leg(args, d, SC, emp, w) for w in ("map", "shuffled")]
             if not args.no_config5:
                 line["config5"] = config5_leg()
+            if not args.no_config1:
+                line["config1"] = config1_leg(d, SC, emp)
             if not args.no_cpu:
                 cb = cpu_baseline(frac=args.cpu_frac, kind=args.cpu_kind)
                 cb.pop("wall_s", None)
@@ -541,6 +568,7 @@ def main():
     ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the short large-connectome leg (configs[4])")
+    ap.add_argument("--no-config1", action="store_true", help="skip the single full-length run through the drop-in surface (configs[0])")
     ap.add_argument("--no-modalities", action="store_true", help="skip the map / shuffled-map sweeps (configs[2], configs[3])")
     args = ap.parse_args()
     if args.cpu_frac is None:

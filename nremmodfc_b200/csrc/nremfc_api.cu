@@ -166,10 +166,18 @@ int nrem_wc_run_f64_ex(const nrem_wc_params* p, const double* CM, const double* 
     const int N = p->nnodes;
     const int threads = (int)round_up(N, 32);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t sm_small = sizeof(double) * 2 * N, sm_big = sm_small + sizeof(double) * (size_t)N * N;
+    const size_t sm_small = sizeof(double) * 4 * N, sm_big = sm_small + sizeof(double) * (size_t)N * N;
+    // in-kernel Philox noise: a second set of warps draws the noise of step t + 1 while the first integrates step t (wc_f64.cuh)
+    static const bool noise_warps_on = []() { const char* e = getenv("NREM_F64_NOISE_WARPS"); return e ? atoi(e) != 0 : true; }();
+    const bool nw = noise_warps_on && !noise;
     if (sm_big <= 200 * 1024) {
-        NREM_CUDA(cudaFuncSetAttribute(wc_run_f64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big));
-        wc_run_f64_kernel<true><<<B, threads, sm_big, st>>>(A);
+        if (nw) {
+            NREM_CUDA(cudaFuncSetAttribute(wc_run_f64_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big));
+            wc_run_f64_kernel<true, true><<<B, 2 * threads, sm_big, st>>>(A);
+        } else {
+            NREM_CUDA(cudaFuncSetAttribute(wc_run_f64_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big));
+            wc_run_f64_kernel<true, false><<<B, threads, sm_big, st>>>(A);
+        }
     } else {
         // SC does not fit shared memory (N > ~150): read a transposed copy from global memory / L2 (coalesced over nodes)
         double* CMt = nullptr;
@@ -177,7 +185,8 @@ int nrem_wc_run_f64_ex(const nrem_wc_params* p, const double* CM, const double* 
         transpose_f64_kernel<<<(N * N + 255) / 256, 256, 0, st>>>(CM, N, CMt);
         NREM_LAUNCHED();
         A.CM = CMt;
-        wc_run_f64_kernel<false><<<B, threads, sm_small, st>>>(A);
+        if (nw && 2 * threads <= 1024) wc_run_f64_kernel<false, true><<<B, 2 * threads, sm_small, st>>>(A);
+        else wc_run_f64_kernel<false, false><<<B, threads, sm_small, st>>>(A);
         NREM_LAUNCHED();
         NREM_CUDA(cudaFreeAsync(CMt, st));
         return NREM_OK;

@@ -25,24 +25,42 @@ struct WcF64Args {
 
 __device__ __forceinline__ double sigm(double x, double sigma, double mu) { return 1.0 / (1.0 + exp(-(x - mu) * sigma)); }
 
-// dynamic smem: Es[2][N] then (CM_SMEM) CMt[N][N] with CMt[j*N+i] = CM[i][j]; otherwise A.CM already IS the transpose
-// (global memory, coalesced over i)
-template <bool CM_SMEM>
-__global__ void __launch_bounds__(CM_SMEM ? 256 : 1024) wc_run_f64_kernel(const WcF64Args A) {
+// one standard-normal draw of the Philox stream for (step, node i): the float64 form of philox.cuh's normals4f
+__device__ __forceinline__ double philox_normal_f64(uint32_t step, int i, uint64_t strm, uint32_t k0, uint32_t k1) {
+    const Philox4 r = philox4x32(step, (uint32_t)(i >> 2), (uint32_t)strm, (uint32_t)(strm >> 32), k0, k1);
+    const bool second = (i & 2) != 0;
+    const double rad = sqrt(-2.0 * log(u23d(second ? r.z : r.x)));
+    const double ang = 6.283185307179586476925286766559 * (u23d(second ? r.w : r.y) - 0.5);
+    double sn, cs;
+    sincos(ang, &sn, &cs);
+    return rad * ((i & 1) ? sn : cs);
+}
+
+// dynamic smem: Es[2][N], nzs[2][N], then (CM_SMEM) CMt[N][N] with CMt[j*N+i] = CM[i][j]; otherwise A.CM already IS the transpose
+// (global memory, coalesced over i).
+// NOISE_WARPS: the block has a second set of round_up(N, 32) threads that only draw the Philox noise of step t + 1 into shared memory
+// while the first set integrates step t.  A float64 step is one long dependent chain (log, sqrt, sincos, two exp, divisions: the
+// time loop of ONE simulation cannot be parallelised), and the noise is the half of it that does not depend on the state; same
+// arithmetic, bit-identical results, the single run of BASELINE configs[0] takes about half the time.
+template <bool CM_SMEM, bool NOISE_WARPS>
+__global__ void __launch_bounds__(CM_SMEM ? 512 : 1024) wc_run_f64_kernel(const WcF64Args A) {
     extern __shared__ double sm64[];
     const nrem_wc_params& p = A.p;
     const int N = p.nnodes;
-    const int i = threadIdx.x;
+    const int NT = NOISE_WARPS ? (int)(blockDim.x >> 1) : (int)blockDim.x;
+    const bool producer = NOISE_WARPS && (int)threadIdx.x >= NT;
+    const int i = producer ? (int)threadIdx.x - NT : (int)threadIdx.x;
     const int b = blockIdx.x;
     double* Es = sm64;
-    double* CMt = sm64 + 2 * N;
+    double* nzs = sm64 + 2 * N;
+    double* CMt = sm64 + 4 * N;
     if (CM_SMEM) {
         for (int k = threadIdx.x; k < N * N; k += blockDim.x) {
             const int r = k / N, c = k % N;
             CMt[c * N + r] = A.CM[k];
         }
     }
-    const bool live = i < N;
+    const bool live = i < N && !producer;
     double E = p.E0, I = p.I0, a = p.a_ie_0;
     // "Any of them can be redefined as a vector of length nnodes" (netwWilsonCowanPlastic.py:21)
     auto npar = [&](int k, double scalar) { return (A.node_par && live) ? A.node_par[(size_t)k * N + i] : scalar; };
@@ -58,12 +76,19 @@ __global__ void __launch_bounds__(CM_SMEM ? 256 : 1024) wc_run_f64_kernel(const 
     const int64_t ns[3] = {p.n1, p.n2, p.n3};
     int64_t step = 0;
     int buf = 0;
+    if (producer && i < N && nsteps_total > 0) nzs[i] = philox_normal_f64(0u, i, strm, k0, k1);
     __syncthreads();
     for (int ph = 0; ph < 3; ++ph) {
         const double tau_ip = p.tau_ip[ph];
         for (int64_t it = 0; it < ns[ph]; ++it, ++step) {
             if (live) Es[buf * N + i] = E;
             __syncthreads();
+            if (producer) {
+                // noise of the NEXT step into the other buffer (its readers passed the barrier above one step ago)
+                if (i < N && step + 1 < nsteps_total) nzs[(buf ^ 1) * N + i] = philox_normal_f64((uint32_t)(step + 1), i, strm, k0, k1);
+                buf ^= 1;
+                continue;
+            }
             if (ph == 2 && live && A.Y && (it % p.downsamp) == 0) {
                 const int64_t r = it / p.downsamp;
                 if (r < A.nrec) {
@@ -94,14 +119,10 @@ __global__ void __launch_bounds__(CM_SMEM ? 256 : 1024) wc_run_f64_kernel(const 
                 double nz;
                 if (nz_base) {
                     nz = nz_base[(size_t)step * N + i];
+                } else if (NOISE_WARPS) {
+                    nz = p.sqdtD * nzs[buf * N + i];
                 } else {
-                    const Philox4 r = philox4x32((uint32_t)step, (uint32_t)(i >> 2), (uint32_t)strm, (uint32_t)(strm >> 32), k0, k1);
-                    const bool second = (i & 2) != 0;
-                    const double rad = sqrt(-2.0 * log(u23d(second ? r.z : r.x)));
-                    const double ang = 6.283185307179586476925286766559 * (u23d(second ? r.w : r.y) - 0.5);
-                    double sn, cs;
-                    sincos(ang, &sn, &cs);
-                    nz = p.sqdtD * rad * ((i & 1) ? sn : cs);
+                    nz = p.sqdtD * philox_normal_f64((uint32_t)step, i, strm, k0, k1);
                 }
                 const double dE = (-E + (1 - rE * E) * sigm(a_ee * E - a * I + G * coup + Pn + nz, sg, mu)) / tauE;
                 const double dI = (-I + (1 - rI * I) * sigm(a_ei * E - a_ii * I, sigmaI, mu)) / tauI;
