@@ -168,8 +168,8 @@ int nrem_wc_run_f64_ex(const nrem_wc_params* p, const double* CM, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm_small = sizeof(double) * 4 * N, sm_big = sm_small + sizeof(double) * (size_t)N * N;
     // in-kernel Philox noise: a second set of warps draws the noise of step t + 1 while the first integrates step t (wc_f64.cuh)
-    static const bool noise_warps_on = []() { const char* e = getenv("NREM_F64_NOISE_WARPS"); return e ? atoi(e) != 0 : true; }();
-    const bool nw = noise_warps_on && !noise;
+    const char* env_nw = getenv("NREM_F64_NOISE_WARPS");          // read per call: tests run both kernels
+    const bool nw = (env_nw ? atoi(env_nw) != 0 : true) && !noise;
     if (sm_big <= 200 * 1024) {
         if (nw) {
             NREM_CUDA(cudaFuncSetAttribute(wc_run_f64_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_big));

@@ -97,6 +97,27 @@ def test_wc_f64_philox_matches_oracle(aal90, oracle_lib):
         assert np.max(np.abs(fin[b] - fo) / np.abs(fo)) < 1e-9
 
 
+def test_wc_f64_noise_warps_are_bit_identical(aal90, monkeypatch):
+    """The float64 run() kernel draws the Philox noise of step t + 1 in a second set of warps while the first set integrates step t
+    (csrc/wc_f64.cuh, NOISE_WARPS): same arithmetic per draw, so Y_t and the final state equal the single-set kernel bit for bit —
+    for the shared-memory SC path (N = 90), a node count that is not a multiple of 32 with per-node vectors, and the transposed
+    global-memory SC path (N = 200)."""
+    from nremmodfc_b200 import ops
+    rng = np.random.default_rng(3)
+    for N in (90, 45, 200):
+        SC = aal90["SC"] if N == 90 else _random_sc(N, N)
+        p = ops.make_params(N, 40, 60, 120, P=0.4, rhoE=0.18, seed=77)
+        G = rng.uniform(0.1, 0.3, (3, N))
+        sg = rng.uniform(7.0, 8.0, (3, N))
+        kw = dict(B=3, streams=[5, 6, 2 ** 40 + 7], want_Y=True, node_params={"P": 0.4 + 0.05 * rng.random(N)} if N == 45 else None)
+        monkeypatch.setenv("NREM_F64_NOISE_WARPS", "0")
+        Y0, f0 = ops.wc_run(p, SC, G, sg, **kw)
+        monkeypatch.setenv("NREM_F64_NOISE_WARPS", "1")
+        Y1, f1 = ops.wc_run(p, SC, G, sg, **kw)
+        assert Y0.shape == (3, 6, 3, N) and np.isfinite(Y0).all()
+        assert np.array_equal(Y0, Y1) and np.array_equal(f0, f1), N
+
+
 def test_wc_derivative_matches_oracle(aal90):
     from nremmodfc_b200 import ops
     from oracle import wc_oracle
