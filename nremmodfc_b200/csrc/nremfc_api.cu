@@ -314,6 +314,7 @@ struct nrem_sweep_plan {
     void* dev;
     int64_t dev_bytes;
     float *state, *SCp, *mapG, *mapS, *par, *Ebuf;
+    float* SCimg;                  // tcgen05 B-operand image of SCp (ld = 96), built by stage_inputs
     int32_t* tile_map;
     uint64_t* streams;
     void* bw_state;
@@ -406,6 +407,7 @@ struct StagePtrs {
     float *state, *SCp, *mapG, *mapS, *par, *Ebuf;
     int32_t* tile_map;
     uint64_t* streams;
+    float* SCimg;      // NULL or room for 2 * kBBytes (ld = 96)
 };
 
 __global__ void fill_strided_f64_kernel(double* dst, int64_t n, int64_t stride, int width, double v) {
@@ -438,6 +440,10 @@ static int stage_inputs(const nrem_wc_params& p, int B, int64_t Bs, int n_maps, 
     else NREM_CUDA(cudaStreamSynchronize(st));
     stage_sc_kernel<<<(ld * ld + 255) / 256, 256, 0, st>>>(CM, N, ld, d.SCp);
     NREM_LAUNCHED();
+    if (d.SCimg && ld == kNPad) {
+        stage_sc_image_kernel<<<(kNPad * kNPad + 255) / 256, 256, 0, st>>>(d.SCp, d.SCimg);
+        NREM_LAUNCHED();
+    }
     stage_maps_kernel<<<(n_maps * ld + 255) / 256, 256, 0, st>>>(mapG, mapS, n_maps, N, ld, d.mapG, d.mapS);
     NREM_LAUNCHED();
     if (homo_hint >= 0) {
@@ -515,6 +521,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
     const int64_t o_state = take(4 * 4 * (int64_t)N * P->Bs);
     const int64_t o_sc = take(4 * (int64_t)P->ld * P->ld);
+    const int64_t o_sci = take(2 * (int64_t)kBBytes);
     const int64_t o_mg = take(4 * (int64_t)n_maps * P->ld);
     const int64_t o_ms = take(4 * (int64_t)n_maps * P->ld);
     const int64_t o_np = take(8 * (int64_t)NREM_NODE_PARAMS * N);
@@ -537,6 +544,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     if (e != cudaSuccess) { delete P; return fail(NREM_ERR_CUDA, "cudaMalloc(sweep plan): %s%s", cudaGetErrorString(e)); }
     char* base = (char*)P->dev;
     P->state = (float*)(base + o_state); P->SCp = (float*)(base + o_sc); P->mapG = (float*)(base + o_mg);
+    P->SCimg = (float*)(base + o_sci);
     P->mapS = (float*)(base + o_ms); P->par = (float*)(base + o_par); P->tile_map = (int32_t*)(base + o_tm);
     P->node_par = (double*)(base + o_np);
     P->streams = (uint64_t*)(base + o_st); P->Ebuf = (float*)(base + o_eb); P->bw_state = base + o_bw;
@@ -635,6 +643,7 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
                      const double* node_par) {
     BatchArgs A;
     A.c = make_const(p);
+    A.SCimg = (d.SCimg && ld == kNPad) ? d.SCimg : nullptr;
     A.state = d.state; A.SCp = d.SCp; A.mapG = d.mapG; A.mapS = d.mapS; A.par = d.par; A.tile_map = d.tile_map;
     A.streams = d.streams; A.Bs = Bs; A.downsamp = p.downsamp; A.homo = homo; A.zero = 0;
     A.ld = ld; A.node_par = node_par; A.dtSim = p.dtSim;
@@ -753,7 +762,7 @@ int nrem_sweep_begin(nrem_sweep_plan* P, const double* CM, const double* mapG, c
     cudaStream_t st = (cudaStream_t)stream;
     SpanTimer span(P, st);
     P->begun = false;
-    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
+    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams, P->SCimg};
     if (P->welchP) NREM_CUDA(cudaMemsetAsync(P->welchP, 0, 4 * P->Bs * (size_t)(P->welch.M + 1), st));
     if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st,
                               homogeneous, P->dflag, P->h_tm, P->tm_done, &P->homo, P->ld)) return rc;
@@ -770,7 +779,7 @@ int nrem_sweep_advance(nrem_sweep_plan* P, int64_t max_chunks, int64_t* h_chunks
     NREM_REQUIRE(P->fed_rows == 0, "this run is being fed with stored samples");
     cudaStream_t st = (cudaStream_t)stream;
     SpanTimer span(P, st);
-    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams};
+    StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams, P->SCimg};
     if (max_chunks > 0)
         if (int rc = integrate(P->p, P->kernel, d, P->B, P->Bs, P->chunk_samples, nullptr, P, st, P->homo, P->cur, max_chunks, P->ld,
                                P->has_node_par ? P->node_par : nullptr)) return rc;
@@ -916,6 +925,7 @@ int nrem_sweep_integrate_f32_ex(const nrem_wc_params* p, int kernel, const doubl
     int64_t off = 0;
     auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
     const int64_t o_sc = take(4 * (int64_t)ld * ld), o_mg = take(4 * (int64_t)n_maps * ld), o_ms = take(4 * (int64_t)n_maps * ld);
+    const int64_t o_sci = take(2 * (int64_t)kBBytes);
     const int64_t o_par = take(4 * 4 * Bs), o_tm = take(4 * (Bs / kTile)), o_st = take(8 * Bs);
     const int kDummyRows = 64;
     const int64_t o_dummy = take(E_samples ? 256 : 4 * (int64_t)kDummyRows * N * Bs);
@@ -924,7 +934,7 @@ int nrem_sweep_integrate_f32_ex(const nrem_wc_params* p, int kernel, const doubl
     NREM_CUDA(cudaMalloc(&dev, (size_t)off));
     char* base = (char*)dev;
     StagePtrs d{(float*)(base + o_st4), (float*)(base + o_sc), (float*)(base + o_mg), (float*)(base + o_ms), (float*)(base + o_par),
-                (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st)};
+                (float*)(base + o_dummy), (int32_t*)(base + o_tm), (uint64_t*)(base + o_st), (float*)(base + o_sci)};
     int homo = 0;
     cudaMemsetAsync(base + o_st4, 0, (size_t)(4 * 4 * (int64_t)N * Bs), st);      // padding simulations the node-lane kernel skips
     int rc = stage_inputs(*p, B, Bs, n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st, -1, nullptr, nullptr, nullptr, &homo, ld);

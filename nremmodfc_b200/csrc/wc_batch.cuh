@@ -32,6 +32,7 @@ struct BatchArgs {
     BatchConst c;
     float* state;              // [4][N][Bs]: E, I, a_ie base, a_ie delta (a_ie = base + delta, see wc_tc.cuh)
     const float* SCp;          // [ld][ld] zero padded (ld = 96; 128 for the node-lane kernel with N > 96)
+    const float* SCimg;        // NULL, or the tcgen05 B-operand image of SCp (wc_tc.cuh: stage_sc_image_kernel), ld = 96 only
     const float* mapG;         // [n_maps][ld]
     const float* mapS;         // [n_maps][ld]
     int ld;

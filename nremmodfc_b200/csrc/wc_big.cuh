@@ -177,14 +177,6 @@ __device__ __forceinline__ BigStep big_step_of(const BigArgs& A, int it, bool pe
     return S;
 }
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// global -> shared bulk copy (TMA engine, no tensor map); completion is signalled on `bar` as transaction bytes
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // wait for two 8-column loads; the registers are in/out operands so that no use can be hoisted above the wait
 __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[8], uint32_t (&q)[8]) {

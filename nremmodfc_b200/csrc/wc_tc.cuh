@@ -38,6 +38,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && ++spins > (1u << 26)) __trap();      // a lost MMA completion must fail loudly, never hang the GPU
     } while (!ok);
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -109,7 +117,21 @@ __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
-// Stage SC (padded [96][96] float32 in global) as the B operand(s).
+// The B operand image of the integrator: SC (padded [96][96] float32) split into TF32 hi / residual lo in the exact shared-memory
+// layout of the MMA, [hi: kBBytes][lo: kBBytes].  Built ONCE per sweep (stage_inputs); every launch then brings it into shared
+// memory with one bulk copy of the TMA engine.
+__global__ void stage_sc_image_kernel(const float* SCp, float* img) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kTcN * kTcK) return;
+    const int n = idx / kTcK, k = idx % kTcK;
+    const float v = SCp[idx];
+    const float h = tf32_rn(v);
+    const int o = (k >> 2) * (int)(kLBO_B / 4) + n * 4 + (k & 3);
+    img[o] = h;
+    img[kBBytes / 4 + o] = v - h;
+}
+
+// Stage SC (padded [96][96] float32 in global) as the B operand(s) with generic loads (self-test, callers without an image).
 template <int NPASS>
 __device__ __forceinline__ void stage_b(const float* SCp, float* Bh, float* Bl, int tid, int nthreads) {
     for (int idx = tid; idx < kTcN * kTcK; idx += nthreads) {
@@ -200,17 +222,26 @@ __global__ void __launch_bounds__((kNPad / CH) * kTile, 1) wc_batch_tc_kernel(co
     const int N = c.N;
     const bool issuer = tid == 4 * (NCHUNK - 1) * 32;      // first thread of the last chunk
 
-    stage_b<NPASS>(A.SCp, Bh, Bl, tid, NT);
+    uint64_t* barB = bar + 1;                                                // SC image landed (bulk copy)
+    if (!A.SCimg) stage_b<NPASS>(A.SCp, Bh, Bl, tid, NT);
     for (int k = tid; k < (int)(kABytes / 4) * (SPLIT ? 2 : 1); k += NT) Ah[k] = 0.f;     // padding columns of A stay 0
     const int mid = A.tile_map[tile];
     if (tid < kNPad) { mG[tid] = A.mapG[mid * kNPad + tid]; mS[tid] = A.mapS[mid * kNPad + tid]; }
     constexpr bool MAPS_TMEM = !HOMO && CH == 24;       // per-node G_i, sigma_i parked in spare TMEM columns (see the E update)
     if (warp == 0) tmem_alloc(tmem_slot, MAPS_TMEM ? kTmemColsMaps : kTmemCols);
-    if (tid == 32) { mbar_init(bar, 1); fence_barrier_init(); }
-    fence_proxy_async();                  // B tile (generic-proxy stores) -> visible to the tensor core's async proxy
+    if (tid == 32) {
+        mbar_init(bar, 1); mbar_init(barB, 1); fence_barrier_init();
+        if (A.SCimg) {                    // SC staged once per sweep as the operand image: ONE TMA bulk copy per launch (hi [+ lo], contiguous)
+            constexpr uint32_t bytes = (SPLIT ? 2u : 1u) * kBBytes;
+            mbar_expect_tx(barB, bytes);
+            bulk_g2s(smem_u32(Bh), A.SCimg, bytes, barB);
+        }
+    }
+    fence_proxy_async();                  // A padding / B tile (generic-proxy stores) -> visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (A.SCimg) mbar_wait(barB, 0);
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t tmem_mine = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chunk * CH);
 
