@@ -216,7 +216,9 @@ int nrem_sweep_integrate_f32_ex(const nrem_wc_params* p, int kernel, const doubl
  * onto the TMEM accumulator, wc_big.cuh).  Same noise stream, a_ie treatment and outputs as nrem_sweep_integrate_f32;
  * mapG/mapS are ONE optional per-node map each (device [N], NULL = ones).  All arrays are device pointers.
  * E_samples [nrec, N, Bpad] (may be NULL), final_state [3, N, Bpad], coup_first (may be NULL) receives the coupling
- * SC.E of the first step [N, Bpad].                                                                              */
+ * SC.E of the first step [N, Bpad].
+ * kernel: precision of the contraction: 2 = one TF32 pass, 3 = 3xTF32, 4 = TF32 + two BF16 correction passes ("tcb"),
+ *         7 = 3xBF16 ("bf3": operands split into two bf16 each, ~4e-6 per product), 0 = auto (= 7).                  */
 int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG, const double* mapS,
                            const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                            const uint64_t* streams, int B, int64_t nrec, float* E_samples, float* final_state,

@@ -973,9 +973,11 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     NREM_REQUIRE(p->nnodes >= 16 && p->nnodes <= 8192, "the large-connectome path supports 16 <= nnodes <= 8192");
     NREM_REQUIRE(!E_samples || nrec >= (p->n3 + p->downsamp - 1) / p->downsamp, "nrec too small");
     NREM_REQUIRE(final_state, "final_state is required");
-    const int k = kernel == 0 ? 4 : kernel;      // auto = TF32 + two BF16 correction passes
-    NREM_REQUIRE(k == 2 || k == 3 || k == 4, "kernel must be auto, tc, tc3 or tcb");
-    const int mixed = k == 4 ? 1 : 0;
+    // auto = 3xBF16 ("bf3", 7); NREM_BIG_KERNEL=<2|3|4|7> overrides auto (read per call)
+    const char* env_kern = getenv("NREM_BIG_KERNEL");
+    const int k = kernel == 0 ? (env_kern ? atoi(env_kern) : 7) : kernel;
+    NREM_REQUIRE(k == 2 || k == 3 || k == 4 || k == 7, "kernel must be auto, tc, tc3, tcb or bf3");
+    const int mixed = k == 4 ? 1 : (k == 7 ? 2 : 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = p->nnodes;
     const int Kpad = (int)round_up(N, 4 * kBigKS), KG = Kpad / 4, slices = (N + kBigNT - 1) / kBigNT;
@@ -1042,10 +1044,12 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             return homoN ? wc_big_step_kernel<M, false, true, P, PR> : wc_big_step_kernel<M, false, false, P, PR>;
         };
         auto pick2 = [&](auto variant) -> void (*)(const BigArgs) {
-            return k == 4 ? pick(std::integral_constant<int, 4>{}, variant)
+            return k == 7 ? pick(std::integral_constant<int, 5>{}, variant)
+                 : k == 4 ? pick(std::integral_constant<int, 4>{}, variant)
                  : k == 3 ? pick(std::integral_constant<int, 3>{}, variant) : pick(std::integral_constant<int, 1>{}, variant);
         };
-        const int smem = pair ? (k == 2 ? big_smem_bytes<1, true>() : big_smem_bytes<3, true>()) : (k == 2 ? big_smem_bytes<1>() : big_smem_bytes<3>());
+        const int smem = pair ? (k == 2 ? big_smem_bytes<1, true>() : k == 7 ? big_smem_bytes<5, true>() : big_smem_bytes<3, true>())
+                              : (k == 2 ? big_smem_bytes<1>() : k == 7 ? big_smem_bytes<5>() : big_smem_bytes<3>());
         const dim3 grid = pair ? dim3((unsigned)tiles, (unsigned)slices) : dim3((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
         const char* env_pdl = getenv("NREM_BIG_PDL");

@@ -27,6 +27,12 @@
 //            accumulation bias of the tensor core itself at N = 1000.  2 TF32 + 2 BF16 MMAs per 16 input nodes (-33 % time).
 //            Images: A = [F: float4 planes][L: bf16 lo(E)][H: bf16 E] with bf16 planes as [tile][KG/2][128 sims][8] (16 B rows),
 //            B likewise [F][H: bf16 S][L: bf16 lo(S)].
+//   5 "bf3"  3xBF16: x = h + l with h = bf16(x), l = bf16(x - h) (16 mantissa bits, |x - h - l| <= 2^-18 |x|);
+//            D = Eh.Sh + El.Sh + Eh.Sl as three kind::f16 MMAs (K = 16) per 16 input nodes = 1.5 TF32-pass equivalents instead of
+//            tcb's 2, and HALF of tcb's operand bytes per K step (4 B per element instead of 8: the FP32 plane no longer goes
+//            through shared memory), which is what the ring-bound MMA phase responds to.  The dropped El.Sl term and the
+//            residuals are ~4e-6 per product with random sign (they average in the N-term sum): below the tensor core's own
+//            accumulation bias.  Same images as tcb: F = E in FP32 (state only, never staged), H, L.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -56,9 +62,15 @@ constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(
 #endif
 constexpr int kBigStagesPair = NREM_BIG_STAGES_PAIR;
 template <int MODE, bool PAIR = false>
-constexpr uint32_t big_stage_bytes() { return (MODE == 1 ? 1u : 2u) * (kBigAStage + (PAIR ? kBigBStage / 2 : kBigBStage)); }
+__host__ __device__ constexpr uint32_t big_stage_bytes() { return ((MODE == 1 || MODE == 5) ? 1u : 2u) * (kBigAStage + (PAIR ? kBigBStage / 2 : kBigBStage)); }
+// ring depth: bf3 stages are half as big as tcb's, so twice as many fit the same shared memory
+#ifndef NREM_BIG_STAGES_BF3_PAIR
+#define NREM_BIG_STAGES_BF3_PAIR 14
+#endif
 template <int MODE, bool PAIR = false>
-constexpr int big_smem_bytes() { return (int)((PAIR ? kBigStagesPair : kBigStages) * big_stage_bytes<MODE, PAIR>()) + 256; }
+__host__ __device__ constexpr int big_stages() { return MODE == 5 ? (PAIR ? NREM_BIG_STAGES_BF3_PAIR : 9) : (PAIR ? kBigStagesPair : kBigStages); }
+template <int MODE, bool PAIR = false>
+constexpr int big_smem_bytes() { return (int)(big_stages<MODE, PAIR>() * big_stage_bytes<MODE, PAIR>()) + 512; }
 constexpr uint32_t kBigIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)((2 * kTile) >> 4) << 24);
 constexpr uint32_t kBigIdescBf16Pair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)((2 * kTile) >> 4) << 24);
 // kind::f16 instruction descriptor: D = F32, A = B = BF16 (format 1), K-major, N = 256, M = 128
@@ -205,16 +217,19 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     extern __shared__ __align__(128) unsigned char smraw[];
     static_assert(!(PAIR && PERSIST), "the CTA-pair kernel is launched once per Euler step");
     constexpr bool SPLIT = MODE == 3;
-    constexpr bool MIXED = MODE == 4;
-    constexpr int NST = PAIR ? kBigStagesPair : kBigStages;
+    constexpr bool BF3 = MODE == 5;
+    constexpr bool MIXED = MODE == 4 || BF3;        // state layout: E in one FP32 plane + two bf16 planes
+    constexpr int NST = big_stages<MODE, PAIR>();
     constexpr int BROWS = PAIR ? kBigNT / 2 : kBigNT;              // B rows (output nodes) this CTA holds in shared memory
     constexpr uint32_t BSTAGE = (uint32_t)kBigKS * BROWS * 16;     // bytes of one FP32 B stage
     constexpr uint32_t LBO_B = (uint32_t)BROWS * 16;
-    constexpr uint32_t STAGE = (MODE == 1 ? 1u : 2u) * (kBigAStage + BSTAGE);
+    constexpr uint32_t STAGE = big_stage_bytes<MODE, PAIR>();
+    static_assert(STAGE == ((MODE == 1 || BF3) ? 1u : 2u) * (kBigAStage + BSTAGE), "stage size");
     constexpr uint32_t IDESC_TF32 = PAIR ? kBigIdescPair : kBigIdesc, IDESC_BF16 = PAIR ? kBigIdescBf16Pair : kBigIdescBf16;
     // stage layout   MODE 1: [A 8K][B 16K]      MODE 3: [Ah 8K][Al 8K][Bh 16K][Bl 16K]
     //                MODE 4: [Af 8K][Al bf16 4K][Ah bf16 4K][Bf 16K][Bh bf16 8K][Bl bf16 8K]        (PAIR: every B part is half as big)
-    constexpr uint32_t OFF_B = (MODE == 1 ? 1u : 2u) * kBigAStage;
+    //                MODE 5: [Al bf16 4K][Ah bf16 4K][Bh bf16 8K][Bl bf16 8K]
+    constexpr uint32_t OFF_B = ((MODE == 1 || BF3) ? 1u : 2u) * kBigAStage;
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NST * STAGE);
     uint64_t* empty = full + NST;
     uint64_t* accum = empty + NST;
@@ -271,13 +286,20 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 mbar_wait(empty + s, (uint32_t)(((ring / NST) & 1) ^ 1));
                 mbar_expect_tx(full + s, STAGE);
                 const uint32_t dst = base + (uint32_t)s * STAGE;
+                if (BF3) {
+                    bulk_g2s(dst, aL + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
+                    bulk_g2s(dst + kBigAStage / 2, aH + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
+                    bulk_g2s(dst + OFF_B, bH + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
+                    bulk_g2s(dst + OFF_B + BSTAGE / 2, bL + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
+                    continue;
+                }
                 bulk_g2s(dst, a0 + (size_t)kt * kBigAStage, kBigAStage, full + s);
                 bulk_g2s(dst + OFF_B, b0 + (size_t)kt * BSTAGE, BSTAGE, full + s);
                 if (SPLIT) {
                     bulk_g2s(dst + kBigAStage, a1 + (size_t)kt * kBigAStage, kBigAStage, full + s);
                     bulk_g2s(dst + OFF_B + BSTAGE, b1 + (size_t)kt * BSTAGE, BSTAGE, full + s);
                 }
-                if (MIXED) {
+                if (MODE == 4) {
                     bulk_g2s(dst + kBigAStage, aL + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
                     bulk_g2s(dst + kBigAStage + kBigAStage / 2, aH + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
                     bulk_g2s(dst + OFF_B + BSTAGE, bH + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
@@ -310,6 +332,19 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 mbar_wait(full + s, (uint32_t)((ring / NST) & 1));
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)s * STAGE;
+                if (BF3) {
+                    const uint64_t aL = umma_desc(sa, kBigLBO_A, kSBO), aH = umma_desc(sa + kBigAStage / 2, kBigLBO_A, kSBO);
+                    const uint64_t bH = umma_desc(sa + OFF_B, LBO_B, kSBO), bL = umma_desc(sa + OFF_B + BSTAGE / 2, LBO_B, kSBO);
+#pragma unroll
+                    for (int k16 = 0; k16 < kBigKS / 4; ++k16) {
+                        const uint64_t da = (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), db = (uint64_t)(k16 * ((2 * LBO_B) >> 4));
+                        if (PAIR) { umma_bf16_2(tmem_d, aH + da, bH + db, IDESC_BF16, acc); umma_bf16_2(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16_2(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
+                        else { umma_bf16(tmem_d, aH + da, bH + db, IDESC_BF16, acc); umma_bf16(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
+                        acc = 1;
+                    }
+                    if (PAIR) umma_commit_2(empty + s); else umma_commit(empty + s);
+                    continue;
+                }
                 const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO);
                 const uint64_t bd_hi = umma_desc(sa + OFF_B, LBO_B, kSBO), bd_lo = umma_desc(sa + OFF_B + BSTAGE, LBO_B, kSBO);
 #pragma unroll
@@ -323,7 +358,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                         acc = 1;
                     }
                 }
-                if (MIXED) {
+                if (MODE == 4) {
                     // one K = 16 BF16 MMA per correction: the bf16 stage arrays are [2 eight-node groups][rows][16 B], i.e. the same
                     // core-matrix geometry (LBO = rows x 16 B, SBO = 128 B) as a K = 8 TF32 slice
                     const uint64_t aL = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO), aH = umma_desc(sa + kBigAStage + kBigAStage / 2, kBigLBO_A, kSBO);
@@ -474,13 +509,23 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                     S.Anext[idx] = make_float4(En[0], En[1], En[2], En[3]);
                     S.Anext[idx + kTile] = make_float4(En[4], En[5], En[6], En[7]);
                     float lo[8];
+                    const uint4 h8 = make_uint4(bf16x2(En[0], En[1]), bf16x2(En[2], En[3]), bf16x2(En[4], En[5]), bf16x2(En[6], En[7]));
+                    if (BF3) {           // residual of the bf16 rounding (exact in FP32)
+                        const uint32_t hw[4] = {h8.x, h8.y, h8.z, h8.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) lo[j] = En[j] - tf32_trunc(En[j]);
+                        for (int j = 0; j < 4; ++j) {
+                            lo[2 * j] = En[2 * j] - __uint_as_float(hw[j] << 16);
+                            lo[2 * j + 1] = En[2 * j + 1] - __uint_as_float(hw[j] & 0xFFFF0000u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) lo[j] = En[j] - tf32_trunc(En[j]);
+                    }
                     uint4* L = reinterpret_cast<uint4*>(S.Anext + plane);
                     uint4* H = L + plane / 2;
                     const size_t i8 = ((size_t)tile * (A.KG / 2) + (size_t)(node0 >> 3)) * kTile + r;
                     L[i8] = make_uint4(bf16x2(lo[0], lo[1]), bf16x2(lo[2], lo[3]), bf16x2(lo[4], lo[5]), bf16x2(lo[6], lo[7]));
-                    H[i8] = make_uint4(bf16x2(En[0], En[1]), bf16x2(En[2], En[3]), bf16x2(En[4], En[5]), bf16x2(En[6], En[7]));
+                    H[i8] = h8;
                 } else {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -541,8 +586,9 @@ __global__ void big_stage_b_kernel(const double* CM, int N, int KG, int slices, 
         __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(Bimg + total);       // [slice][KG/2][256][8]
         __nv_bfloat16* L = H + total;
         const size_t o = ((blk * (KG / 2) + (kg >> 1)) * R + row) * 8 + (size_t)((kg & 1) * 4 + kk);
-        H[o] = __float2bfloat16_rn(v);
-        L[o] = __float2bfloat16_rn(v - tf32_trunc(v));
+        const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+        H[o] = hb;
+        L[o] = __float2bfloat16_rn(mixed == 2 ? v - __bfloat162float(hb) : v - tf32_trunc(v));
     }
 }
 
@@ -565,7 +611,7 @@ __global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, fl
     for (int j = 0; j < 4; ++j) {
         const bool live = kg * 4 + j < c.N;
         e[j] = live ? (mixed ? c.E0 : tf32_rn(c.E0)) : 0.f;
-        l[j] = live ? (mixed ? c.E0 - tf32_trunc(c.E0) : c.E0 - e[j]) : 0.f;
+        l[j] = live ? (mixed == 2 ? c.E0 - __bfloat162float(__float2bfloat16_rn(c.E0)) : mixed ? c.E0 - tf32_trunc(c.E0) : c.E0 - e[j]) : 0.f;
         i[j] = live ? c.I0 : 0.f;
         a[j] = live ? c.a0 : 0.f;
     }

@@ -254,7 +254,7 @@ def kuramoto(bold, device=None):
     return (float(out[0, 0]), float(out[0, 1])) if sq else (out[:, 0], out[:, 1])
 
 
-KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3, "tcb": 4, "node32": 5, "node16": 6}
+KERNELS = {"auto": 0, "fma": 1, "tc": 2, "tc3": 3, "tcb": 4, "node32": 5, "node16": 6, "bf3": 7}
 KERNEL_NAMES = {v: k for k, v in KERNELS.items()}
 
 

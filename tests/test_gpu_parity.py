@@ -610,7 +610,8 @@ def _random_sc(N, seed):
 
 @pytest.mark.parametrize("N,B,kernel,hetero", [(300, 130, "tc3", False), (300, 130, "tc", True), (1000, 256, "tc3", True),
                                                (528, 128, "tc3", False), (300, 130, "tcb", False), (1000, 256, "tcb", True),
-                                               (528, 128, "auto", True)])
+                                               (528, 128, "auto", True), (300, 130, "bf3", False), (1000, 256, "bf3", True),
+                                               (64, 128, "bf3", True)])
 def test_large_connectome_integrator_vs_oracle(N, B, kernel, hetero, oracle_lib):
     """BASELINE configs[4] fast path (csrc/wc_big.cuh: one launch per Euler step, tcgen05 GEMM of the whole batch with the
     node update fused onto the TMEM accumulator) against the float64 oracle on the same Philox streams: recorded E rows,
@@ -664,7 +665,7 @@ def test_large_connectome_persistent_cluster_mode_is_bit_identical(monkeypatch):
     assert np.array_equal(E0, E1) and np.array_equal(f0, f1)
 
 
-@pytest.mark.parametrize("kernel,B", [("tcb", 1100), ("tc3", 256), ("tc", 384)])
+@pytest.mark.parametrize("kernel,B", [("tcb", 1100), ("tc3", 256), ("tc", 384), ("bf3", 1100), ("bf3", 384)])
 def test_large_connectome_cta_pair_mode_is_bit_identical(kernel, B, monkeypatch):
     """CTA pairs (tcgen05 cta_group::2: two 128-simulation tiles per M = 256 MMA, each CTA staging half of the SC tile) against
     single-CTA MMAs: same products, same accumulation order, so E samples, final state and the first coupling must be identical
