@@ -1017,11 +1017,12 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
         BigArgs A;
         A.c = make_const(*p);
         big_init_kernel<<<(unsigned)((nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)nf4, KG, mixed, (float4*)(base + o_a0), nf4, (float4*)(base + o_i),
-                                                                      (float4*)(base + o_ab));
+                                                                      (float4*)(base + o_ab), (float4*)(base + o_ad));
         NREM_LAUNCHED();
         float4* img[2] = {(float4*)(base + o_a0), (float4*)(base + o_a1)};
         A.Bimg = (const float4*)(base + o_b);
         A.I4 = (float4*)(base + o_i); A.ab4 = (float4*)(base + o_ab); A.ad4 = (float4*)(base + o_ad);
+        A.Fst = img[0];                  // bf3: E in FP32, updated in place (plane F of image 0)
         A.par = (const float*)(base + o_par); A.streams = (const uint64_t*)(base + o_st);
         A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
         A.Bs = Bs; A.Bo = round_up(B, kTile); A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
@@ -1138,7 +1139,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             fprintf(stderr, "[NREM_BIG_DBG]   next step's earliest 'dependency wait over': %8.2f\n", ((double)t0next - (double)t0min) * 1e-3);
         }
         const int64_t n = (int64_t)N * A.Bo;
-        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, A.Bo, mixed, (const float*)img[total & 1], nf4 * 4, (const float*)A.I4,
+        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, A.Bo, mixed, (const float*)img[mixed == 2 ? 0 : (total & 1)], nf4 * 4, (const float*)A.I4,
                                                                       (const float*)A.ab4, (const float*)A.ad4, final_state);
         NREM_LAUNCHED();
         return NREM_OK;

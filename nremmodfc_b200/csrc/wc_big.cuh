@@ -32,7 +32,11 @@
 //            tcb's 2, and HALF of tcb's operand bytes per K step (4 B per element instead of 8: the FP32 plane no longer goes
 //            through shared memory), which is what the ring-bound MMA phase responds to.  The dropped El.Sl term and the
 //            residuals are ~4e-6 per product with random sign (they average in the N-term sum): below the tensor core's own
-//            accumulation bias.  Same images as tcb: F = E in FP32 (state only, never staged), H, L.
+//            accumulation bias.  Same images as tcb: F = E in FP32 (state only, never staged), H, L.  Two footprint cuts
+//            (the 124 MB of state + operands of configs[4] no longer fit the L2; ncu: half of the sectors missed): the F
+//            plane is private to its owner thread, so it is updated IN PLACE (plane F of image 0; only H and L ping-pong),
+//            and a_base is kept as bf16 (2 B; a_ie = a_base + delta with delta = the exact FP32 remainder, re-split every
+//            kRecombine steps), which takes the working set to 93 MB.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -127,7 +131,8 @@ struct BigArgs {
     float4* Anext;             // E(t+1) image
     const float4* Bimg;
     float4* I4;
-    float4* ab4;               // a_ie base
+    float4* ab4;               // a_ie base (bf3: bf16, addressed as uint2[])
+    float4* Fst;               // bf3: the FP32 plane of E, updated in place by its owner thread (plane F of image 0)
     float4* ad4;               // a_ie delta (a_ie = base + delta, see wc_tc.cuh)
     const float* par;          // [4][Bs]: G0, dG, sigma0, dsigm
     const uint64_t* streams;   // [Bs]
@@ -409,10 +414,13 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
             const size_t idx0 = rowbase + (size_t)(node_base >> 2) * kTile;
             auto load4 = [&](int qd, BigQuad& s) {
                 const size_t idx = idx0 + (size_t)qd * kTile;
-                s.eh = S.Acur[idx];
+                s.eh = BF3 ? A.Fst[idx] : S.Acur[idx];
                 if (!MIXED) s.el = S.Acur[plane + idx];
                 s.i = A.I4[idx];
-                s.b = A.ab4[idx];
+                if (BF3) {               // bf16 x 4 -> FP32
+                    const uint2 u = reinterpret_cast<const uint2*>(A.ab4)[idx];
+                    s.b = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+                } else s.b = A.ab4[idx];
                 s.d = A.ad4[idx];
             };
             BigQuad cur, n1;
@@ -433,7 +441,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 for (int j = 0; j < 4; ++j) {
                     const int node = node0 + j;
                     const bool live = FULL || node < N;
-                    if (S.recombine) { ab[j] += ad[j]; ad[j] = 0.f; }
+                    if (S.recombine) {
+                        ab[j] += ad[j];
+                        if (BF3) { const float t = ab[j]; ab[j] = __uint_as_float(bf16x2(0.f, t) & 0xFFFF0000u); ad[j] = t - ab[j]; }      // bf16 base + exact remainder
+                        else ad[j] = 0.f;
+                    }
                     if (live && S.rec && sim < A.Bo) A.Ebuf[((size_t)S.row * N + node) * A.Bo + sim] = E[j];      // state BEFORE the update (WC:129-130)
                     float xp = fmaf(c.sq, z[j], Pmu);
                     xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(c.a_ee, E[j], xp)));
@@ -447,7 +459,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 }
                 A.I4[idx] = make_float4(I[0], I[1], I[2], I[3]);
                 A.ad4[idx] = make_float4(ad[0], ad[1], ad[2], ad[3]);
-                if (S.recombine) A.ab4[idx] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+                if (S.recombine) {
+                    if (BF3) reinterpret_cast<uint2*>(A.ab4)[idx] = make_uint2((__float_as_uint(ab[0]) >> 16) | (__float_as_uint(ab[1]) & 0xFFFF0000u),
+                                                                               (__float_as_uint(ab[2]) >> 16) | (__float_as_uint(ab[3]) & 0xFFFF0000u));
+                    else A.ab4[idx] = make_float4(ab[0], ab[1], ab[2], ab[3]);
+                }
                 tmem_st4(tmem_mine + kBigNT + 4 * qd, xp4);
                 cur = n1;
             }
@@ -462,7 +478,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                                                  // round trip is longer than one group's arithmetic
             auto loadE = [&](int g, float4 (&e)[NE]) {
                 const size_t idx = rowbase + (size_t)((node_base + 8 * g) >> 2) * kTile;
-                e[0] = S.Acur[idx]; e[1] = S.Acur[idx + kTile];
+                if (BF3) { e[0] = A.Fst[idx]; e[1] = A.Fst[idx + kTile]; }
+                else { e[0] = S.Acur[idx]; e[1] = S.Acur[idx + kTile]; }
                 if (!MIXED) { e[NE - 2] = S.Acur[plane + idx]; e[NE - 1] = S.Acur[plane + idx + kTile]; }
             };
             // software pipeline: the TMEM loads (coupling + xp) and the E(t) loads of group g + 1 are in flight while group g is computed
@@ -506,8 +523,9 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                     }
                 }
                 if (MIXED) {
-                    S.Anext[idx] = make_float4(En[0], En[1], En[2], En[3]);
-                    S.Anext[idx + kTile] = make_float4(En[4], En[5], En[6], En[7]);
+                    float4* Fn = BF3 ? A.Fst : S.Anext;
+                    Fn[idx] = make_float4(En[0], En[1], En[2], En[3]);
+                    Fn[idx + kTile] = make_float4(En[4], En[5], En[6], En[7]);
                     float lo[8];
                     const uint4 h8 = make_uint4(bf16x2(En[0], En[1]), bf16x2(En[2], En[3]), bf16x2(En[4], En[5]), bf16x2(En[6], En[7]));
                     if (BF3) {           // residual of the bf16 rounding (exact in FP32)
@@ -600,7 +618,7 @@ __global__ void big_stage_maps_kernel(const double* mapG, const double* mapS, in
 }
 
 // initial condition (netwWilsonCowanPlastic.py:90-99) into the images; every array was zeroed before
-__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, float4* A0, size_t plane, float4* I4, float4* ab4) {
+__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, float4* A0, size_t plane, float4* I4, float4* ab4, float4* ad4) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index [tile][kg][r]
     if (idx >= nf4) return;
     const int kg = (int)((idx / kTile) % KG);
@@ -626,7 +644,14 @@ __global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, fl
         for (int j = 0; j < 4; ++j) { L[o + j] = __float2bfloat16_rn(l[j]); H[o + j] = __float2bfloat16_rn(e[j]); }
     }
     I4[idx] = make_float4(i[0], i[1], i[2], i[3]);
-    ab4[idx] = make_float4(a[0], a[1], a[2], a[3]);
+    if (mixed == 2) {            // bf16 base (the remainder a0 - bf16(a0) goes to the delta array: see big_init_delta below)
+        reinterpret_cast<uint2*>(ab4)[idx] = make_uint2((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a[0])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a[1])) << 16),
+                                                        (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a[2])) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a[3])) << 16));
+        float4 d;
+        d.x = a[0] - __bfloat162float(__float2bfloat16_rn(a[0])); d.y = a[1] - __bfloat162float(__float2bfloat16_rn(a[1]));
+        d.z = a[2] - __bfloat162float(__float2bfloat16_rn(a[2])); d.w = a[3] - __bfloat162float(__float2bfloat16_rn(a[3]));
+        ad4[idx] = d;
+    } else ab4[idx] = make_float4(a[0], a[1], a[2], a[3]);
 }
 
 // images -> final state [3][N][Bs] (E, I, a_ie), simulation fastest
@@ -640,7 +665,8 @@ __global__ void big_export_kernel(int N, int KG, int64_t Bo, int mixed, const fl
     const size_t src = (((size_t)(sim / kTile) * KG + (node >> 2)) * kTile + (size_t)(sim % kTile)) * 4 + (node & 3);
     fin[k] = mixed ? Aimg[src] : Aimg[src] + Aimg[plane_f + src];
     fin[(int64_t)N * Bo + k] = I[src];
-    fin[2 * (int64_t)N * Bo + k] = ab[src] + ad[src];
+    const float base = mixed == 2 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ab)[src]) : ab[src];
+    fin[2 * (int64_t)N * Bo + k] = base + ad[src];
 }
 
 }  // namespace nrem
