@@ -97,12 +97,14 @@ int64_t nrem_filt_scratch_bytes(int B, int64_t T, int N, int64_t Neq, int64_t ds
 int nrem_filtfilt_decimate_f64(const double* bold, int B, int64_t T, int N, int64_t Neq, int64_t ds,
                                const double* h_b, const double* h_a, double* out, void* scratch, void* stream);
 
-/* Replaces np.corrcoef(BOLD.T) (whole_sweep_both.py:81).  bold [B,J,N] -> fc [B,N,N].          */
+/* Replaces np.corrcoef(BOLD.T) (whole_sweep_both.py:81).  bold [B,J,N] -> fc [B,N,N].  Any N: up to 128 nodes one CTA per
+ * simulation with the matrix in shared memory, above that one CTA per 32 x 32 tile.                                   */
 int nrem_fc_f64(const double* bold, int B, int64_t J, int N, double* fc, void* stream);
 
 /* Replaces utils.get_all_metrics(sFC, empFC, data_range=1) for K targets (utils.py:42-50,
  * whole_sweep_both.py:83-86) and sFC.mean() (whole_sweep_both.py:94).
- *   fc [B,N,N], emp [K,N,N] -> gof [B,K,4] = (corr, euc, ssim, new_metric); meanfc [B] (may be NULL). */
+ *   fc [B,N,N], emp [K,N,N] -> gof [B,K,4] = (corr, euc, ssim, new_metric); meanfc [B] (may be NULL).
+ * N >= 7 (the 7 x 7 SSIM window); above 128 nodes both matrices stay in global memory (one CTA per simulation and target). */
 int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, double data_range,
                  double* gof, double* meanfc, void* stream);
 
@@ -125,7 +127,9 @@ typedef struct nrem_sweep_plan nrem_sweep_plan;   /* opaque; owns device scratch
 
 typedef struct nrem_sweep_opts {
     int32_t kernel;          /* 0 = auto, 1 = CUDA-core coupling, 2 = tcgen05 (TF32) coupling, 3 = tcgen05 3xTF32,            */
-                             /* 5 / 6 = node-lane tcgen05 3xTF32 with 32 / 16 simulations per CTA (see nrem_sweep_kernel)       */
+                             /* 5 / 6 = node-lane tcgen05 3xTF32 with 32 / 16 simulations per CTA (see nrem_sweep_kernel),      */
+                             /* 7 = large-connectome integrator (one launch per Euler step, 16 <= nnodes <= 8192, one map pair): */
+                             /*     what auto picks above 128 nodes                                                              */
     int32_t bold_f32;        /* 1 = Balloon-Windkessel state in float32 (default 0 = float64)      */
     int32_t chunk_samples;   /* stored samples per launch of the integrator (0 = default)           */
     int32_t want_fc;         /* 1 = also return the FC matrices                                      */
@@ -139,6 +143,9 @@ typedef struct nrem_sweep_opts {
     double  welch_fs;        /* sampling rate of the stored samples, 1/dt (reference: 500 Hz)                 */
 } nrem_sweep_opts;
 
+/* 7 <= nnodes <= 8192.  Up to 128 nodes the register-resident integrators (kernels 1-6) run; above that (any other parcellation,
+ * BASELINE configs[4]) the plan integrates with the large-connectome kernel of nrem_big_integrate_f32 and runs the same
+ * BOLD -> filter -> FC -> GoF -> Kuramoto chain, FC / GoF in batches of simulations (n_maps must be 1, no per-node tables). */
 int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, int n_maps, int K,
                       nrem_sweep_plan** plan);
 int nrem_sweep_destroy(nrem_sweep_plan* plan);
@@ -173,7 +180,7 @@ int nrem_sweep_set_node_params(nrem_sweep_plan* plan, const double* node_params,
 /* The integrator kernel the plan resolved to (1 CUDA-core, 2 tcgen05 TF32, 3 tcgen05 3xTF32: 128 simulations per CTA, a
  * thread = one simulation x 24 nodes; 5 / 6 node-lane tcgen05 3xTF32: 32 / 16 simulations per CTA, a thread = one node x 8 / 4
  * simulations, nnodes <= 128).  opts.kernel = 0 picks 6 or 5 for batches too small to fill the SMs with 128-simulation tiles,
- * for nnodes > 96 and for per-node parameter tables, else 3.                                                                   */
+ * for nnodes > 96 and for per-node parameter tables, else 3; 7 = large-connectome integrator (nnodes > 128).                  */
 int nrem_sweep_kernel(const nrem_sweep_plan* plan);
 int nrem_sweep_begin(nrem_sweep_plan* plan, const double* CM, const double* mapG, const double* mapS,
                      const double* G0, const double* dG, const double* sigma0, const double* dsigma,

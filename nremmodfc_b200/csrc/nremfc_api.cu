@@ -246,7 +246,16 @@ int nrem_filtfilt_decimate_f64(const double* bold, int B, int64_t T, int N, int6
 int nrem_fc_f64(const double* bold, int B, int64_t J, int N, double* fc, void* stream) {
     NREM_REQUIRE(bold && fc, "null array");
     NREM_REQUIRE(B >= 1 && J >= 2, "bad shape");
-    NREM_REQUIRE(N >= 1 && N <= 128, "fc supports 1 <= N <= 128");
+    NREM_REQUIRE(N >= 1 && N <= 32768, "fc supports 1 <= N <= 32768");
+    if (N > 128) {       // any parcellation: tiled kernel (fc_gof.cuh)
+        const unsigned nt = (unsigned)((N + 31) / 32);
+        for (int b0 = 0; b0 < B; b0 += 65535) {          // grid.z limit
+            const int nb = std::min(B - b0, 65535);
+            fc_big_f64_kernel<<<dim3(nt, nt, (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(bold + (size_t)b0 * J * N, J, N, fc + (size_t)b0 * N * N);
+            NREM_LAUNCHED();
+        }
+        return NREM_OK;
+    }
     const size_t sm = sizeof(double) * (2 * N + kFcTile * N);
     fc_f64_kernel<<<B, kFcThreads, sm, (cudaStream_t)stream>>>(bold, J, N, fc);
     NREM_LAUNCHED();
@@ -257,7 +266,13 @@ int nrem_gof_f64(const double* fc, const double* emp, int B, int K, int N, doubl
                  double* gof, double* meanfc, void* stream) {
     NREM_REQUIRE(fc && emp && gof, "null array");
     NREM_REQUIRE(B >= 1 && K >= 1, "bad shape");
-    NREM_REQUIRE(N >= 7 && N <= 128, "gof supports 7 <= N <= 128");
+    NREM_REQUIRE(N >= 7 && N <= 32768, "gof supports 7 <= N <= 32768");
+    NREM_REQUIRE(K <= 65535, "at most 65535 targets");
+    if (N > 128) {       // any parcellation: both matrices stay in global memory
+        gof_big_f64_kernel<<<dim3((unsigned)B, (unsigned)K), 1024, 0, (cudaStream_t)stream>>>(fc, emp, K, N, data_range, gof, meanfc);
+        NREM_LAUNCHED();
+        return NREM_OK;
+    }
     const int emp_smem = N <= 118 ? 1 : 0;          // both matrices fit shared memory up to N = 118; above, the target is read through L1/L2
     const size_t sm = sizeof(double) * ((emp_smem ? 2 : 1) * (size_t)N * N + 40);
     NREM_CUDA(cudaFuncSetAttribute(gof_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -302,6 +317,7 @@ struct IntegCursor {
     int first;          // 1 until the first launch (which starts from E0, I0, a_ie_0 instead of the stored state)
 };
 
+struct BigRun;
 struct nrem_sweep_plan {
     nrem_wc_params p;
     nrem_sweep_opts o;
@@ -326,6 +342,10 @@ struct nrem_sweep_plan {
     int ld;                        // padded node count of the staged SC / maps (96 or 128)
     double* node_par;              // [NREM_NODE_PARAMS][N] per-node parameter table, valid when has_node_par
     bool has_node_par;
+    // kernel 7 (more than 128 nodes): the large-connectome integrator (wc_big.cuh) feeds the same BOLD / filter / FC / GoF chain
+    BigRun* big;
+    void* big_dev;
+    int64_t fc_batch;              // simulations per FC / GoF pass of nrem_sweep_finish (the FC scratch holds this many N x N matrices)
     // pinned host staging of the per-tile map ids, and the event after which it may be overwritten
     int32_t* h_tm;
     cudaEvent_t tm_done;
@@ -364,6 +384,145 @@ static BatchConst make_const(const nrem_wc_params& p) {
     c.k0 = (uint32_t)p.seed; c.k1 = (uint32_t)(p.seed >> 32);
     c.N = p.nnodes;
     return c;
+}
+
+// ---- large-connectome integrator (wc_big.cuh): one launch per Euler step ----------------------------------------------------
+// Device state + launch configuration of one batch; used by nrem_big_integrate_f32 and by sweep plans with more than 128 nodes.
+struct BigRun {
+    int k = 0, mixed = 0, N = 0, Kpad = 0, KG = 0, slices = 0, tiles = 0, smem = 0;
+    bool pair = false, pdl = true, want_persist = false;
+    int64_t Bs = 0, bytes = 0;
+    size_t nf4 = 0;
+    int64_t o_a0 = 0, o_a1 = 0, o_i = 0, o_ab = 0, o_ad = 0, o_b = 0, o_par = 0, o_st = 0, o_mg = 0, o_ms = 0;
+    char* base = nullptr;
+    float4* img[2] = {nullptr, nullptr};
+    BigArgs A;
+    dim3 grid;
+    void (*kern)(const BigArgs) = nullptr;          // one launch per step (single CTA or CTA pair)
+    void (*kern_persist)(const BigArgs) = nullptr;
+};
+
+// Sizes and offsets (R.bytes of device memory, 256-byte aligned pieces).  kernel: 0 = auto (3xBF16, "bf3"; NREM_BIG_KERNEL overrides).
+static int big_layout(BigRun& R, const nrem_wc_params& p, int kernel, int B) {
+    const char* env_kern = getenv("NREM_BIG_KERNEL");
+    R.k = kernel == 0 ? (env_kern ? atoi(env_kern) : 7) : kernel;
+    NREM_REQUIRE(R.k == 2 || R.k == 3 || R.k == 4 || R.k == 7, "kernel must be auto, tc, tc3, tcb or bf3");
+    R.mixed = R.k == 4 ? 1 : (R.k == 7 ? 2 : 0);
+    R.N = p.nnodes;
+    R.Kpad = (int)round_up(R.N, 4 * kBigKS); R.KG = R.Kpad / 4; R.slices = (R.N + kBigNT - 1) / kBigNT;
+    // CTA pairs (cta_group::2, two 128-simulation tiles per M = 256 MMA) whenever the batch has an even number of tiles, or enough
+    // tiles that one padding tile is cheap; NREM_BIG_PAIR=0 / 1 forces the choice (read per call: tests run both).  The persistent
+    // cluster mode keeps single-CTA MMAs.
+    const char* env_pair = getenv("NREM_BIG_PAIR");
+    const char* env_persist = getenv("NREM_BIG_PERSIST");              // read per call so that tests can exercise both modes
+    R.want_persist = env_persist ? atoi(env_persist) != 0 : false;    // measured 3-10 % slower than per-step launches + PDL
+    const int64_t tiles0 = round_up(B, kTile) / kTile;
+    R.pair = !R.want_persist && (env_pair ? atoi(env_pair) != 0 : (tiles0 % 2 == 0 || tiles0 >= 9));
+    R.Bs = round_up(B, R.pair ? 2 * kTile : kTile);
+    R.tiles = (int)(R.Bs / kTile);
+    R.nf4 = (size_t)R.tiles * R.KG * kTile;                            // float4 per state plane
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
+    R.o_a0 = take(2 * 16 * (int64_t)R.nf4); R.o_a1 = take(2 * 16 * (int64_t)R.nf4);
+    R.o_i = take(16 * (int64_t)R.nf4); R.o_ab = take(16 * (int64_t)R.nf4); R.o_ad = take(16 * (int64_t)R.nf4);
+    R.o_b = take(2 * 16 * (int64_t)R.slices * R.KG * kBigNT);
+    R.o_par = take(4 * 4 * R.Bs); R.o_st = take(8 * R.Bs); R.o_mg = take(4 * R.Kpad); R.o_ms = take(4 * R.Kpad);
+    R.bytes = off;
+    const char* env_pdl = getenv("NREM_BIG_PDL");
+    R.pdl = env_pdl ? atoi(env_pdl) != 0 : true;
+    return NREM_OK;
+}
+
+// Stages SC, the maps, the per-simulation parameters and the initial condition into R.base (R.bytes of device memory) and prepares
+// the kernel arguments.  homo: 1 = no per-node maps (scalar G, sigma per simulation), 0 = maps.
+static int big_stage(BigRun& R, const nrem_wc_params& p, void* dev, const double* CM, const double* mapG, const double* mapS,
+                     const double* G0, const double* dG, const double* sigma0, const double* dsigma, const uint64_t* streams,
+                     int B, int homo, cudaStream_t st) {
+    R.base = (char*)dev;
+    char* base = R.base;
+    const int N = R.N, KG = R.KG, slices = R.slices;
+    NREM_CUDA(cudaMemsetAsync(dev, 0, (size_t)R.o_b, st));            // images and state: padding nodes stay zero for ever
+    const size_t nb = (size_t)slices * KG * kBigNT * 4;
+    big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, R.mixed, R.pair ? kBigNT / 2 : kBigNT, (float*)(base + R.o_b));
+    NREM_LAUNCHED();
+    big_stage_maps_kernel<<<(R.Kpad + 255) / 256, 256, 0, st>>>(mapG, mapS, N, R.Kpad, (float*)(base + R.o_mg), (float*)(base + R.o_ms));
+    NREM_LAUNCHED();
+    stage_par_kernel<<<(unsigned)((R.Bs + 255) / 256), 256, 0, st>>>(G0, dG, sigma0, dsigma, streams, B, R.Bs, (float*)(base + R.o_par),
+                                                                    (uint64_t*)(base + R.o_st));
+    NREM_LAUNCHED();
+    BigArgs& A = R.A;
+    A.c = make_const(p);
+    big_init_kernel<<<(unsigned)((R.nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)R.nf4, KG, R.mixed, (float4*)(base + R.o_a0), R.nf4, (float4*)(base + R.o_i),
+                                                                    (float4*)(base + R.o_ab), (float4*)(base + R.o_ad));
+    NREM_LAUNCHED();
+    R.img[0] = (float4*)(base + R.o_a0); R.img[1] = (float4*)(base + R.o_a1);
+    A.Bimg = (const float4*)(base + R.o_b);
+    A.I4 = (float4*)(base + R.o_i); A.ab4 = (float4*)(base + R.o_ab); A.ad4 = (float4*)(base + R.o_ad);
+    A.Fst = R.img[0];                  // bf3: E in FP32, updated in place (plane F of image 0)
+    A.par = (const float*)(base + R.o_par); A.streams = (const uint64_t*)(base + R.o_st);
+    A.mapG = (const float*)(base + R.o_mg); A.mapS = (const float*)(base + R.o_ms);
+    A.Bs = R.Bs; A.Bo = round_up(B, kTile); A.tiles = R.tiles; A.slices = slices; A.KG = KG; A.homo = homo;
+    A.Ebuf = nullptr; A.dbg = nullptr; A.coup = nullptr;
+    A.img[0] = R.img[0]; A.img[1] = R.img[1];
+    A.n1 = (uint32_t)p.n1; A.n12 = (uint32_t)(p.n1 + p.n2); A.downsamp = p.downsamp;
+    for (int ph = 0; ph < 3; ++ph) A.kA3[ph] = (float)(p.dtSim / p.tau_ip[ph]);
+    A.nsteps = 1;
+    const bool fullN = N % 8 == 0, homoN = homo != 0;
+    const int k = R.k;
+    // variant: 0 = one launch per step, 1 = persistent cluster, 2 = one launch per step with CTA pairs
+    auto pick = [&](auto mode, auto variant) -> void (*)(const BigArgs) {
+        constexpr int M = decltype(mode)::value;
+        constexpr bool P = decltype(variant)::value == 1, PR = decltype(variant)::value == 2;
+        if (fullN) return homoN ? wc_big_step_kernel<M, true, true, P, PR> : wc_big_step_kernel<M, true, false, P, PR>;
+        return homoN ? wc_big_step_kernel<M, false, true, P, PR> : wc_big_step_kernel<M, false, false, P, PR>;
+    };
+    auto pick2 = [&](auto variant) -> void (*)(const BigArgs) {
+        return k == 7 ? pick(std::integral_constant<int, 5>{}, variant)
+             : k == 4 ? pick(std::integral_constant<int, 4>{}, variant)
+             : k == 3 ? pick(std::integral_constant<int, 3>{}, variant) : pick(std::integral_constant<int, 1>{}, variant);
+    };
+    R.smem = R.pair ? (k == 2 ? big_smem_bytes<1, true>() : k == 7 ? big_smem_bytes<5, true>() : big_smem_bytes<3, true>())
+                    : (k == 2 ? big_smem_bytes<1>() : k == 7 ? big_smem_bytes<5>() : big_smem_bytes<3>());
+    R.grid = R.pair ? dim3((unsigned)R.tiles, (unsigned)slices) : dim3((unsigned)slices, (unsigned)R.tiles);
+    R.kern_persist = pick2(std::integral_constant<int, 1>{});
+    R.kern = R.pair ? pick2(std::integral_constant<int, 2>{}) : pick2(std::integral_constant<int, 0>{});
+    NREM_CUDA(cudaFuncSetAttribute(R.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R.smem));
+    return NREM_OK;
+}
+
+// One Euler step (global step index s) as one launch.  Ebuf/row: where E(t) of a recorded step goes (rec), [rows][N][Bo].
+static int big_step(BigRun& R, const nrem_wc_params& p, int64_t s, bool rec, float* Ebuf, int64_t row, float* coup,
+                    unsigned long long* dbg, cudaStream_t st) {
+    BigArgs& A = R.A;
+    const int ph = s < p.n1 ? 0 : (s < p.n1 + p.n2 ? 1 : 2);
+    A.Acur = R.img[s & 1]; A.Anext = R.img[(s + 1) & 1];
+    A.step = (uint32_t)s;
+    A.kA = A.kA3[ph];
+    A.recombine = (s != 0 && (s & (int64_t)(kRecombine - 1)) == 0) ? 1 : 0;
+    A.rec = rec ? 1 : 0;
+    A.Ebuf = Ebuf;
+    A.row = rec ? row : 0;
+    A.coup = coup;
+    A.dbg = dbg;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = R.grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
+    cfg.dynamicSmemBytes = (size_t)R.smem;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (R.pair) {       // tiles 2p, 2p+1 of a node slice = one cluster = one CTA pair
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (R.pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    NREM_CUDA(cudaLaunchKernelEx(&cfg, R.kern, A));
+    NREM_LAUNCHED();
+    return NREM_OK;
 }
 
 // Simulations per CTA of an integrator kernel: the simulation-lane kernels (1 = CUDA-core, 2/3 = tcgen05) use tiles of 128,
@@ -473,10 +632,16 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     if (int rc = check_params(p)) return rc;
     NREM_REQUIRE(o && plan, "null argument");
     NREM_REQUIRE(B >= 1 && n_maps >= 1 && K >= 1, "bad shape");
-    NREM_REQUIRE(p->nnodes >= 7 && p->nnodes <= 128, "the sweep supports 7 <= nnodes <= 128");
+    NREM_REQUIRE(p->nnodes >= 7 && p->nnodes <= 8192, "the sweep supports 7 <= nnodes <= 8192");
     NREM_REQUIRE(o->bold_downsamp >= 1 && o->Neq >= 0, "bad BOLD options");
-    NREM_REQUIRE(o->kernel >= 0 && o->kernel <= 6 && o->kernel != 4, "kernel must be 0 (auto), 1, 2, 3, 5 or 6");
-    NREM_REQUIRE(p->nnodes <= kNPad || o->kernel == 0 || o->kernel >= 5, "more than 96 nodes need the node-lane kernel (kernel 0, 5 or 6)");
+    NREM_REQUIRE(o->kernel >= 0 && o->kernel <= 7 && o->kernel != 4, "kernel must be 0 (auto), 1, 2, 3, 5, 6 or 7");
+    // more than 128 nodes (other parcellations, BASELINE configs[4]): the large-connectome integrator (kernel 7, one launch per
+    // Euler step) feeds the same BOLD / filter / FC / GoF chain; it can also be asked for explicitly from 16 nodes on
+    const bool big = p->nnodes > 128 || o->kernel == 7;
+    NREM_REQUIRE(p->nnodes <= 128 || o->kernel == 0 || o->kernel == 7, "more than 128 nodes need the large-connectome integrator (kernel 0 or 7)");
+    NREM_REQUIRE(!big || p->nnodes >= 16, "the large-connectome integrator needs at least 16 nodes");
+    NREM_REQUIRE(!big || n_maps == 1, "the large-connectome integrator takes one (mapG, mapS) pair per sweep");
+    NREM_REQUIRE(big || p->nnodes <= kNPad || o->kernel == 0 || o->kernel >= 5, "more than 96 nodes need the node-lane kernel (kernel 0, 5 or 6)");
     nrem_sweep_plan* P = new (std::nothrow) nrem_sweep_plan();
     if (!P) return fail(NREM_ERR_ARG, "out of host memory%s%s");
     P->p = *p; P->o = *o; P->B = B; P->n_maps = n_maps; P->K = K; P->N = p->nnodes; P->dev = nullptr;
@@ -484,17 +649,25 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->h_tm = nullptr; P->tm_done = nullptr; P->begun = false; P->fed_rows = 0; P->homo = 0;
     P->cur = IntegCursor{0, 0, 0, 1};
     P->node_par = nullptr; P->has_node_par = false;
-    P->kernel = resolve_kernel(o->kernel, p->nnodes, B, false);
+    P->big = nullptr; P->big_dev = nullptr; P->fc_batch = B;
+    if (big) {
+        P->big = new (std::nothrow) BigRun();
+        if (!P->big) { delete P; return fail(NREM_ERR_ARG, "out of host memory%s%s"); }
+        if (int rc = big_layout(*P->big, *p, 0, B)) { delete P->big; delete P; return rc; }
+        if (p->nnodes > 128) P->fc_batch = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 31) / (8 * (int64_t)p->nnodes * p->nnodes)));
+        if (const char* e = getenv("NREM_SWEEP_FC_BATCH")) P->fc_batch = std::max<int64_t>(1, std::min<int64_t>(B, atoll(e)));      // tests
+    }
+    P->kernel = big ? 7 : resolve_kernel(o->kernel, p->nnodes, B, false);
     P->tile_sims = kernel_tile_sims(P->kernel);
     P->ld = p->nnodes > kNPad ? 128 : kNPad;
     P->Bs = round_up(B, kTile); P->tiles = P->Bs / kTile;
     P->T = (p->n3 + p->downsamp - 1) / p->downsamp;
     P->Tf = P->T - o->Neq;
-    if (P->Tf < 32) { delete P; return fail(NREM_ERR_ARG, "fewer than 32 BOLD samples after the Neq cut%s%s"); }
+    if (P->Tf < 32) { delete P->big; delete P; return fail(NREM_ERR_ARG, "fewer than 32 BOLD samples after the Neq cut%s%s"); }
     P->J = (P->Tf + o->bold_downsamp - 1) / o->bold_downsamp;
     P->nth = (int64_t)P->N * P->Bs;
     P->chunk_samples = o->chunk_samples > 0 ? o->chunk_samples : 250;
-    if (int rc = prepare_filter(o->b, o->a, P->Tf, o->bold_downsamp, P->fh)) { delete P; return rc; }
+    if (int rc = prepare_filter(o->b, o->a, P->Tf, o->bold_downsamp, P->fh)) { delete P->big; delete P; return rc; }
     P->ring_rows = P->chunk_samples; P->welch_nseg = 0; P->welchP = nullptr; P->welch.L = 0; P->wring = nullptr;
     std::vector<float> h_win;
     std::vector<float2> h_tw, h_tw2;
@@ -505,7 +678,7 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
         while (ok && m % 4 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 4; m /= 4; }
         while (ok && m % 2 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 2; m /= 2; }
         while (ok && m % 5 == 0 && ns < kWelchMaxStages) { P->welch.radix[ns++] = 5; m /= 5; }
-        if (!ok || m != 1) { delete P; return fail(NREM_ERR_UNSUPPORTED, "welch: need even nperseg <= T with nperseg/2 = 2^a 5^b <= 2560 and a multiple of chunk_samples%s%s"); }
+        if (!ok || m != 1) { delete P->big; delete P; return fail(NREM_ERR_UNSUPPORTED, "welch: need even nperseg <= T with nperseg/2 = 2^a 5^b <= 2560 and a multiple of chunk_samples%s%s"); }
         P->welch.L = L; P->welch.M = M; P->welch.nstages = ns;
         P->welch_nseg = (int)((P->T - L) / M + 1);
         P->welch_smem = 2 * kWelchSims * M * 8 + M * 8 + kWelchSims * (M + 1) * 4 + 160;
@@ -532,7 +705,8 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int64_t o_bw = take((o->bold_f32 ? 4 : 8) * 4 * P->nth);
     const int64_t o_fs = take(8 * filt_scratch_doubles(P->nth, P->J, o->bold_downsamp));
     const int64_t o_bd = take(8 * (int64_t)B * P->J * N);
-    const int64_t o_fc = take(8 * (int64_t)B * N * N);
+    const int64_t o_fc = take(8 * P->fc_batch * N * N);
+    const int64_t o_big = take(P->big ? P->big->bytes : 0);
     const int64_t o_obs = take(8 * 3 * (int64_t)B);
     const int64_t o_hil = take(8 * std::max<int64_t>(P->J, 1));
     const int64_t o_flag = take(16);
@@ -541,8 +715,9 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     const int64_t o_wp = take(WL ? 4 * P->Bs * (int64_t)(WM + 1) : 0), o_ww = take(4 * (int64_t)WL), o_wt = take(8 * (int64_t)WM), o_wt2 = take(8 * (int64_t)(WM + 1));
     P->dev_bytes = off;
     cudaError_t e = cudaMalloc(&P->dev, (size_t)off);
-    if (e != cudaSuccess) { delete P; return fail(NREM_ERR_CUDA, "cudaMalloc(sweep plan): %s%s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { delete P->big; delete P; return fail(NREM_ERR_CUDA, "cudaMalloc(sweep plan): %s%s", cudaGetErrorString(e)); }
     char* base = (char*)P->dev;
+    if (P->big) P->big_dev = base + o_big;
     P->state = (float*)(base + o_state); P->SCp = (float*)(base + o_sc); P->mapG = (float*)(base + o_mg);
     P->SCimg = (float*)(base + o_sci);
     P->mapS = (float*)(base + o_ms); P->par = (float*)(base + o_par); P->tile_map = (int32_t*)(base + o_tm);
@@ -591,6 +766,7 @@ int nrem_sweep_destroy(nrem_sweep_plan* plan) {
     for (cudaEvent_t e : plan->gjoin) cudaEventDestroy(e);
     for (cudaStream_t g : plan->gstreams) cudaStreamDestroy(g);
     if (plan->gfork) cudaEventDestroy(plan->gfork);
+    delete plan->big;
     delete plan;
     return NREM_OK;
 }
@@ -739,8 +915,38 @@ struct SpanTimer {
     ~SpanTimer() { if (end) cudaEventRecord(end, st); }
 };
 
+// Kernel 7: the same chunk structure as integrate(), with one launch per Euler step (wc_big.cuh) instead of one per chunk; the E
+// samples of a chunk go through the plan's ring buffer to the BOLD / forward-filter kernel on the same stream.
+static int big_advance(nrem_sweep_plan* P, int64_t max_chunks, cudaStream_t st) {
+    const nrem_wc_params& p = P->p;
+    const int64_t ns[3] = {p.n1, p.n2, p.n3};
+    const int64_t chunk_steps = (int64_t)P->chunk_samples * p.downsamp;
+    IntegCursor& cur = P->cur;
+    for (int64_t done = 0; cur.ph < 3 && done < max_chunks;) {
+        const int ph = cur.ph;
+        const int64_t i0 = cur.i0;
+        if (i0 >= ns[ph]) { ++cur.ph; cur.i0 = 0; continue; }
+        const int64_t n = std::min(chunk_steps, ns[ph] - i0);
+        const int64_t row_base = i0 / p.downsamp;              // chunks start on a multiple of downsamp
+        const int rows = (int)((n + p.downsamp - 1) / p.downsamp);
+        const int64_t ring_row0 = row_base % P->ring_rows;
+        for (int64_t j = 0; j < n; ++j) {
+            const bool rec = ph == 2 && (i0 + j) % p.downsamp == 0;
+            if (int rc = big_step(*P->big, p, cur.step + j, rec, P->Ebuf, ring_row0 + ((i0 + j) / p.downsamp - row_base), nullptr, nullptr, st)) return rc;
+        }
+        if (ph == 2)
+            if (int rc = launch_bold_chunk(P, P->Ebuf + ring_row0 * (int64_t)P->N * P->Bs, rows, row_base, 0, P->Bs, st)) return rc;
+        cur.i0 += n; cur.step += n; cur.first = 0;
+        ++done;
+    }
+    while (cur.ph < 3 && cur.i0 >= ns[cur.ph]) { ++cur.ph; cur.i0 = 0; }
+    return NREM_OK;
+}
+
 int nrem_sweep_set_node_params(nrem_sweep_plan* P, const double* node_params, void* stream) {
     NREM_REQUIRE(P, "plan is null");
+    NREM_REQUIRE(P->kernel != 7 || !node_params, "per-node parameter tables are not available on the large-connectome integrator (more than 128 nodes)");
+    if (P->kernel == 7) return NREM_OK;
     if (!node_params) { P->has_node_par = false; P->kernel = resolve_kernel(P->o.kernel, P->N, P->B, false); P->tile_sims = kernel_tile_sims(P->kernel); return NREM_OK; }
     NREM_REQUIRE(P->o.kernel == 0 || P->o.kernel >= 5, "per-node parameter tables need the node-lane kernel (kernel 0, 5 or 6)");
     NREM_CUDA(cudaMemcpyAsync(P->node_par, node_params, sizeof(double) * NREM_NODE_PARAMS * (size_t)P->N, cudaMemcpyDeviceToDevice,
@@ -764,6 +970,17 @@ int nrem_sweep_begin(nrem_sweep_plan* P, const double* CM, const double* mapG, c
     P->begun = false;
     StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams, P->SCimg};
     if (P->welchP) NREM_CUDA(cudaMemsetAsync(P->welchP, 0, 4 * P->Bs * (size_t)(P->welch.M + 1), st));
+    if (P->kernel == 7) {
+        if (h_map_id) for (int b = 0; b < P->B; ++b) if (h_map_id[b] != 0) return fail(NREM_ERR_ARG, "map_id out of range%s%s");
+        // homogeneous = -1 (unknown): the map kernel is used; it is exact for maps of ones, too
+        P->homo = homogeneous == 1 ? 1 : 0;
+        if (int rc = big_stage(*P->big, P->p, P->big_dev, CM, P->homo ? nullptr : mapG, P->homo ? nullptr : mapS, G0, dG, sigma0, dsigma, streams,
+                               P->B, P->homo, st)) return rc;
+        P->cur = IntegCursor{0, 0, 0, 1};
+        P->fed_rows = 0;
+        P->begun = true;
+        return NREM_OK;
+    }
     if (int rc = stage_inputs(P->p, P->B, P->Bs, P->n_maps, CM, mapG, mapS, G0, dG, sigma0, dsigma, h_map_id, streams, d, st,
                               homogeneous, P->dflag, P->h_tm, P->tm_done, &P->homo, P->ld)) return rc;
     P->cur = IntegCursor{0, 0, 0, 1};
@@ -780,7 +997,9 @@ int nrem_sweep_advance(nrem_sweep_plan* P, int64_t max_chunks, int64_t* h_chunks
     cudaStream_t st = (cudaStream_t)stream;
     SpanTimer span(P, st);
     StagePtrs d{P->state, P->SCp, P->mapG, P->mapS, P->par, P->Ebuf, P->tile_map, P->streams, P->SCimg};
-    if (max_chunks > 0)
+    if (max_chunks > 0 && P->kernel == 7) {
+        if (int rc = big_advance(P, max_chunks, st)) return rc;
+    } else if (max_chunks > 0)
         if (int rc = integrate(P->p, P->kernel, d, P->B, P->Bs, P->chunk_samples, nullptr, P, st, P->homo, P->cur, max_chunks, P->ld,
                                P->has_node_par ? P->node_par : nullptr)) return rc;
     if (h_chunks_left) {
@@ -821,7 +1040,9 @@ int nrem_sweep_finish(nrem_sweep_plan* P, const double* emp, double* gof, double
                                                                          P->J * N, N, 1, P->B);
     NREM_LAUNCHED();
     double* fcd = fc ? fc : P->fc;
-    if (int rc = nrem_fc_f64(P->bold_dec, P->B, P->J, N, fcd, stream)) return rc;
+    const bool batched = !fc && P->fc_batch < P->B;        // large N: the FC scratch holds fc_batch matrices at a time
+    if (!batched)
+        if (int rc = nrem_fc_f64(P->bold_dec, P->B, P->J, N, fcd, stream)) return rc;
     double* meanfc = nullptr;
     if (extra) {
         const double nan_v = __builtin_nan("");
@@ -845,7 +1066,15 @@ int nrem_sweep_finish(nrem_sweep_plan* P, const double* emp, double* gof, double
         }
         meanfc = P->obs + 2 * (int64_t)P->B;         // mean FC -> extra[b][0]
     }
-    if (int rc = nrem_gof_f64(fcd, emp, P->B, P->K, N, 1.0, gof, meanfc, stream)) return rc;
+    if (!batched) {
+        if (int rc = nrem_gof_f64(fcd, emp, P->B, P->K, N, 1.0, gof, meanfc, stream)) return rc;
+    } else {
+        for (int64_t b0 = 0; b0 < P->B; b0 += P->fc_batch) {
+            const int nb = (int)std::min<int64_t>(P->fc_batch, P->B - b0);
+            if (int rc = nrem_fc_f64(P->bold_dec + b0 * P->J * N, nb, P->J, N, P->fc, stream)) return rc;
+            if (int rc = nrem_gof_f64(P->fc, emp, nb, P->K, N, 1.0, gof + b0 * P->K * 4, meanfc ? meanfc + b0 : nullptr, stream)) return rc;
+        }
+    }
     if (extra) {
         NREM_CUDA(cudaMemcpy2DAsync(extra, 4 * sizeof(double), meanfc, sizeof(double), sizeof(double), P->B,
                                     cudaMemcpyDeviceToDevice, st));
@@ -962,7 +1191,6 @@ int nrem_sweep_integrate_f32_ex(const nrem_wc_params* p, int kernel, const doubl
     return NREM_OK;
 }
 
-// Large-connectome integrator (wc_big.cuh): one launch per Euler step.
 int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG, const double* mapS,
                            const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                            const uint64_t* streams, int B, int64_t nrec, float* E_samples, float* final_state,
@@ -973,147 +1201,57 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     NREM_REQUIRE(p->nnodes >= 16 && p->nnodes <= 8192, "the large-connectome path supports 16 <= nnodes <= 8192");
     NREM_REQUIRE(!E_samples || nrec >= (p->n3 + p->downsamp - 1) / p->downsamp, "nrec too small");
     NREM_REQUIRE(final_state, "final_state is required");
-    // auto = 3xBF16 ("bf3", 7); NREM_BIG_KERNEL=<2|3|4|7> overrides auto (read per call)
-    const char* env_kern = getenv("NREM_BIG_KERNEL");
-    const int k = kernel == 0 ? (env_kern ? atoi(env_kern) : 7) : kernel;
-    NREM_REQUIRE(k == 2 || k == 3 || k == 4 || k == 7, "kernel must be auto, tc, tc3, tcb or bf3");
-    const int mixed = k == 4 ? 1 : (k == 7 ? 2 : 0);
+    BigRun R;
+    if (int rc = big_layout(R, *p, kernel, B)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int N = p->nnodes;
-    const int Kpad = (int)round_up(N, 4 * kBigKS), KG = Kpad / 4, slices = (N + kBigNT - 1) / kBigNT;
-    // CTA pairs (cta_group::2, two 128-simulation tiles per M = 256 MMA) whenever the batch has an even number of tiles, or enough
-    // tiles that one padding tile is cheap; NREM_BIG_PAIR=0 / 1 forces the choice (read per call: tests run both).  The persistent
-    // cluster mode keeps single-CTA MMAs.
-    const char* env_pair = getenv("NREM_BIG_PAIR");
-    const char* env_persist = getenv("NREM_BIG_PERSIST");              // read per call so that tests can exercise both modes
-    const bool want_persist = env_persist ? atoi(env_persist) != 0 : false;   // measured 3-10 % slower than per-step launches + PDL
-    const int64_t tiles0 = round_up(B, kTile) / kTile;
-    const bool pair = !want_persist && (env_pair ? atoi(env_pair) != 0 : (tiles0 % 2 == 0 || tiles0 >= 9));
-    const int64_t Bs = round_up(B, pair ? 2 * kTile : kTile);
-    const int tiles = (int)(Bs / kTile);
-    const size_t nf4 = (size_t)tiles * KG * kTile;                      // float4 per state plane
-    int64_t off = 0;
-    auto take = [&](int64_t bytes) { int64_t o0 = off; off = round_up(off + bytes, 256); return o0; };
-    const int64_t o_a0 = take(2 * 16 * (int64_t)nf4), o_a1 = take(2 * 16 * (int64_t)nf4);
-    const int64_t o_i = take(16 * (int64_t)nf4), o_ab = take(16 * (int64_t)nf4), o_ad = take(16 * (int64_t)nf4);
-    const int64_t o_b = take(2 * 16 * (int64_t)slices * KG * kBigNT);
-    const int64_t o_par = take(4 * 4 * Bs), o_st = take(8 * Bs), o_mg = take(4 * Kpad), o_ms = take(4 * Kpad);
     void* dev = nullptr;
-    NREM_CUDA(cudaMalloc(&dev, (size_t)off));
-    char* base = (char*)dev;
+    NREM_CUDA(cudaMalloc(&dev, (size_t)R.bytes));
     int rc = NREM_OK;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     auto body = [&]() -> int {
-        NREM_CUDA(cudaMemsetAsync(dev, 0, (size_t)o_b, st));            // images and state: padding nodes stay zero for ever
-        const size_t nb = (size_t)slices * KG * kBigNT * 4;
-        big_stage_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(CM, N, KG, slices, mixed, pair ? kBigNT / 2 : kBigNT, (float*)(base + o_b));
-        NREM_LAUNCHED();
-        big_stage_maps_kernel<<<(Kpad + 255) / 256, 256, 0, st>>>(mapG, mapS, N, Kpad, (float*)(base + o_mg), (float*)(base + o_ms));
-        NREM_LAUNCHED();
-        stage_par_kernel<<<(unsigned)((Bs + 255) / 256), 256, 0, st>>>(G0, dG, sigma0, dsigma, streams, B, Bs, (float*)(base + o_par),
-                                                                      (uint64_t*)(base + o_st));
-        NREM_LAUNCHED();
-        BigArgs A;
-        A.c = make_const(*p);
-        big_init_kernel<<<(unsigned)((nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)nf4, KG, mixed, (float4*)(base + o_a0), nf4, (float4*)(base + o_i),
-                                                                      (float4*)(base + o_ab), (float4*)(base + o_ad));
-        NREM_LAUNCHED();
-        float4* img[2] = {(float4*)(base + o_a0), (float4*)(base + o_a1)};
-        A.Bimg = (const float4*)(base + o_b);
-        A.I4 = (float4*)(base + o_i); A.ab4 = (float4*)(base + o_ab); A.ad4 = (float4*)(base + o_ad);
-        A.Fst = img[0];                  // bf3: E in FP32, updated in place (plane F of image 0)
-        A.par = (const float*)(base + o_par); A.streams = (const uint64_t*)(base + o_st);
-        A.mapG = (const float*)(base + o_mg); A.mapS = (const float*)(base + o_ms);
-        A.Bs = Bs; A.Bo = round_up(B, kTile); A.tiles = tiles; A.slices = slices; A.KG = KG; A.homo = (!mapG && !mapS) ? 1 : 0;
-        A.Ebuf = E_samples;
+        if (int r = big_stage(R, *p, dev, CM, mapG, mapS, G0, dG, sigma0, dsigma, streams, B, (!mapG && !mapS) ? 1 : 0, st)) return r;
+        BigArgs& A = R.A;
+        const int slices = R.slices, tiles = R.tiles;
         // NREM_BIG_DBG=<step>: phase timing of that Euler step (globaltimer stamps per CTA, printed to stderr) -- developer switch
         const char* env_dbg = getenv("NREM_BIG_DBG");
         const int64_t dbg_step = env_dbg ? atoll(env_dbg) : -1;
         unsigned long long* dbg_dev = nullptr;
-        A.dbg = nullptr;
         if (dbg_step >= 0) {
             NREM_CUDA(cudaMalloc((void**)&dbg_dev, sizeof(unsigned long long) * 8 * (size_t)slices * tiles * 2));
             NREM_CUDA(cudaMemsetAsync(dbg_dev, 0, sizeof(unsigned long long) * 8 * (size_t)slices * tiles * 2, st));
         }
-        const bool fullN = N % 8 == 0, homoN = A.homo != 0;
-        // variant: 0 = one launch per step, 1 = persistent cluster, 2 = one launch per step with CTA pairs
-        auto pick = [&](auto mode, auto variant) -> void (*)(const BigArgs) {
-            constexpr int M = decltype(mode)::value;
-            constexpr bool P = decltype(variant)::value == 1, PR = decltype(variant)::value == 2;
-            if (fullN) return homoN ? wc_big_step_kernel<M, true, true, P, PR> : wc_big_step_kernel<M, true, false, P, PR>;
-            return homoN ? wc_big_step_kernel<M, false, true, P, PR> : wc_big_step_kernel<M, false, false, P, PR>;
-        };
-        auto pick2 = [&](auto variant) -> void (*)(const BigArgs) {
-            return k == 7 ? pick(std::integral_constant<int, 5>{}, variant)
-                 : k == 4 ? pick(std::integral_constant<int, 4>{}, variant)
-                 : k == 3 ? pick(std::integral_constant<int, 3>{}, variant) : pick(std::integral_constant<int, 1>{}, variant);
-        };
-        const int smem = pair ? (k == 2 ? big_smem_bytes<1, true>() : k == 7 ? big_smem_bytes<5, true>() : big_smem_bytes<3, true>())
-                              : (k == 2 ? big_smem_bytes<1>() : k == 7 ? big_smem_bytes<5>() : big_smem_bytes<3>());
-        const dim3 grid = pair ? dim3((unsigned)tiles, (unsigned)slices) : dim3((unsigned)slices, (unsigned)tiles);
         const int64_t total = p->n1 + p->n2 + p->n3;
-        const char* env_pdl = getenv("NREM_BIG_PDL");
-        const bool pdl = env_pdl ? atoi(env_pdl) != 0 : true;
-        A.img[0] = img[0]; A.img[1] = img[1];
-        A.n1 = (uint32_t)p->n1; A.n12 = (uint32_t)(p->n1 + p->n2); A.downsamp = p->downsamp;
-        for (int ph = 0; ph < 3; ++ph) A.kA3[ph] = (float)(p->dtSim / p->tau_ip[ph]);
-        A.nsteps = 1;
         // Persistent mode (NREM_BIG_PERSIST=1): the node slices of a tile form one thread-block cluster that runs all steps (one
         // barrier.cluster per step, no launches).  Needs the cluster to fit the portable size and to be schedulable with this much
         // shared memory.  Correct (tests run both modes) but on B200 it measured 42.6-44.1 us/step against 41.3-42.2 for one launch
         // per step with programmatic dependent launch (tc3: 52-54 vs 47.7), so it is not the default.
-        bool persist = want_persist && slices <= 8 && total > 0 && total <= 0x7fffffff;    // nsteps is an int
-        void (*kern_p)(const BigArgs) = pick2(std::integral_constant<int, 1>{});
+        bool persist = R.want_persist && slices <= 8 && total > 0 && total <= 0x7fffffff;    // nsteps is an int
         cudaLaunchConfig_t cfgp = {};
         cudaLaunchAttribute atp[1];
         if (persist) {
-            NREM_CUDA(cudaFuncSetAttribute(kern_p, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            cfgp.gridDim = grid; cfgp.blockDim = dim3(kBigThreads); cfgp.stream = st; cfgp.dynamicSmemBytes = (size_t)smem;
+            NREM_CUDA(cudaFuncSetAttribute(R.kern_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, R.smem));
+            cfgp.gridDim = R.grid; cfgp.blockDim = dim3(kBigThreads); cfgp.stream = st; cfgp.dynamicSmemBytes = (size_t)R.smem;
             atp[0].id = cudaLaunchAttributeClusterDimension;
             atp[0].val.clusterDim.x = (unsigned)slices; atp[0].val.clusterDim.y = 1; atp[0].val.clusterDim.z = 1;
             cfgp.attrs = atp; cfgp.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, kern_p, &cfgp) != cudaSuccess || nclusters < 1) { cudaGetLastError(); persist = false; }
+            if (cudaOccupancyMaxActiveClusters(&nclusters, R.kern_persist, &cfgp) != cudaSuccess || nclusters < 1) { cudaGetLastError(); persist = false; }
         }
         NREM_CUDA(cudaEventRecord(t0, st));
         if (persist) {
             A.step = 0; A.nsteps = (int)std::min<int64_t>(total, 0x7fffffff);
             A.Acur = nullptr; A.Anext = nullptr; A.kA = 0.f; A.recombine = 0; A.rec = 0; A.row = 0; A.coup = coup_first;
-            NREM_CUDA(cudaLaunchKernelEx(&cfgp, kern_p, A));
+            A.Ebuf = E_samples;
+            NREM_CUDA(cudaLaunchKernelEx(&cfgp, R.kern_persist, A));
             NREM_LAUNCHED();
         } else {
-            void (*kern)(const BigArgs) = pair ? pick2(std::integral_constant<int, 2>{}) : pick2(std::integral_constant<int, 0>{});
-            NREM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             for (int64_t s = 0; s < total; ++s) {
-                const int ph = s < p->n1 ? 0 : (s < p->n1 + p->n2 ? 1 : 2);
                 const int64_t it = s - p->n1 - p->n2;
-                A.Acur = img[s & 1]; A.Anext = img[(s + 1) & 1];
-                A.step = (uint32_t)s;
-                A.kA = A.kA3[ph];
-                A.recombine = (s != 0 && (s & (int64_t)(kRecombine - 1)) == 0) ? 1 : 0;
-                A.rec = (E_samples && ph == 2 && it % p->downsamp == 0) ? 1 : 0;
-                A.row = A.rec ? it / p->downsamp : 0;
-                A.coup = s == 0 ? coup_first : nullptr;
-                A.dbg = (dbg_dev && (s == dbg_step || s == dbg_step + 1)) ? dbg_dev + (s - dbg_step) * 8 * (size_t)slices * tiles : nullptr;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = grid; cfg.blockDim = dim3(kBigThreads); cfg.stream = st;
-                cfg.dynamicSmemBytes = (size_t)smem;
-                cudaLaunchAttribute at[2];
-                int na = 0;
-                if (pair) {       // tiles 2p, 2p+1 of a node slice = one cluster = one CTA pair
-                    at[na].id = cudaLaunchAttributeClusterDimension;
-                    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
-                    ++na;
-                }
-                if (pdl) {
-                    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                    at[na].val.programmaticStreamSerializationAllowed = 1;
-                    ++na;
-                }
-                cfg.attrs = at; cfg.numAttrs = na;
-                NREM_CUDA(cudaLaunchKernelEx(&cfg, kern, A));
-                NREM_LAUNCHED();
+                const bool rec = E_samples && it >= 0 && it % p->downsamp == 0;
+                unsigned long long* dbg = (dbg_dev && (s == dbg_step || s == dbg_step + 1)) ? dbg_dev + (s - dbg_step) * 8 * (size_t)slices * tiles : nullptr;
+                if (int r = big_step(R, *p, s, rec, E_samples, rec ? it / p->downsamp : 0, s == 0 ? coup_first : nullptr, dbg, st)) return r;
             }
         }
         NREM_CUDA(cudaEventRecord(t1, st));
@@ -1139,7 +1277,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
             fprintf(stderr, "[NREM_BIG_DBG]   next step's earliest 'dependency wait over': %8.2f\n", ((double)t0next - (double)t0min) * 1e-3);
         }
         const int64_t n = (int64_t)N * A.Bo;
-        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, KG, A.Bo, mixed, (const float*)img[mixed == 2 ? 0 : (total & 1)], nf4 * 4, (const float*)A.I4,
+        big_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(N, R.KG, A.Bo, R.mixed, (const float*)R.img[R.mixed == 2 ? 0 : (total & 1)], R.nf4 * 4, (const float*)A.I4,
                                                                       (const float*)A.ab4, (const float*)A.ad4, final_state);
         NREM_LAUNCHED();
         return NREM_OK;

@@ -181,7 +181,7 @@ def test_short_input_is_rejected():
         ops.filtfilt_decimate(np.zeros((2010, 3)), b, a)
 
 
-@pytest.mark.parametrize("N,J", [(90, 298), (90, 11), (17, 64), (128, 40)])
+@pytest.mark.parametrize("N,J", [(90, 298), (90, 11), (17, 64), (128, 40), (129, 298), (300, 298), (1000, 77)])
 def test_fc_matches_numpy(N, J):
     from nremmodfc_b200 import ops
     rng = np.random.default_rng(N + J)
@@ -192,7 +192,7 @@ def test_fc_matches_numpy(N, J):
     assert np.array_equal(fc, np.transpose(fc, (0, 2, 1)))
 
 
-@pytest.mark.parametrize("N", [90, 30, 7])
+@pytest.mark.parametrize("N", [90, 30, 7, 128, 200, 419])
 def test_gof_matches_oracle(N, aal90):
     from nremmodfc_b200 import ops
     from oracle import bold_oracle
@@ -645,6 +645,59 @@ def test_large_connectome_integrator_vs_oracle(N, B, kernel, hetero, oracle_lib)
                                stream=int(streams[b]), p=po, want="final")
         assert np.max(np.abs(E[:, :, b] - Yo[:, 0, :]) / np.abs(Yo[:, 0, :])) < tol
         assert np.max(np.abs(fin[:, :, b] - fo) / np.abs(fo)) < tol
+
+
+@pytest.mark.parametrize("N,hetero", [(200, False), (300, True)])
+def test_sweep_beyond_128_nodes_vs_oracle(N, hetero, oracle_lib, monkeypatch):
+    """Fused sweep for a parcellation beyond 128 nodes (netwWilsonCowanPlastic.py:64-68 allows any nnodes; BASELINE configs[4]): the plan
+    resolves to the large-connectome integrator (one launch per Euler step, wc_big.cuh) and feeds the same BOLD -> filter -> FC -> GoF ->
+    Kuramoto chain.  (a) E samples of the plan's integrator == nrem_big_integrate_f32 on the same streams, checked against the float64
+    oracle; (b) the stages against the oracle fed with the SAME samples (float64 BOLD state: 1e-6); (c) FC / GoF computed in batches of
+    simulations (the N x N matrices of a large batch do not fit at once) == all at once; (d) a sliced run == one call."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle, wc_oracle
+    n1, n2, n3 = 100, 300, 6000
+    p = ops.make_params(N, n1, n2, n3, P=0.4, rhoE=0.18, seed=12)
+    po = wc_oracle.params(P=0.4, rhoE=0.18)
+    rng = np.random.default_rng(N)
+    SC = _random_sc(N, N + 7)
+    emp = np.stack([np.corrcoef(rng.normal(size=(N, 80)) + rng.normal(size=(1, 80))) for _ in range(2)])
+    B = 140
+    dG, ds = np.linspace(-0.1, 0.3, B), np.linspace(0.2, -0.2, B)
+    streams = np.arange(B, dtype=np.uint64) * 5 + 3
+    G0, s0 = np.full(B, 0.16), np.full(B, 7.68)
+    mG = rng.uniform(0.5, 1.5, N) if hetero else None
+    mS = rng.uniform(0.8, 1.2, N) if hetero else None
+    kw = dict(kernel="auto", bold_f32=False, Neq=100, bold_downsamp=10, chunk_samples=37)
+    plan = sweep.SweepPlan(p, B, n_maps=1, K=2, **kw)
+    assert plan.kernel_name == "bf3"
+    out = plan.run(SC, emp, G0, dG, s0, ds, streams, mG, mS, None, True)
+    assert out["gof"].shape == (B, 2, 4) and out["fc"].shape == (B, N, N) and np.isfinite(out["gof"]).all()
+    Eg, _ = ops.big_integrate_f32(p, SC, G0, dG, s0, ds, mG, mS, streams, kernel="bf3")
+    for k in (0, 127, 139):
+        G = 0.16 + dG[k] * (mG if hetero else np.ones(N))
+        sg = 7.68 + ds[k] * (mS if hetero else np.ones(N))
+        Eo = oracle_lib.wc_run(SC, G, sg, n1, n2, n3, seed=12, stream=int(streams[k]), p=po, want="E")
+        assert (np.abs(Eg[0, :, k] - Eo[0]) / np.maximum(np.abs(Eo[0]), 0.05)).max() < 5e-4         # (a) first recorded row, see test_sweep_pipeline_vs_oracle
+        E = Eg[:, :, k].astype(np.float64)
+        bold = bold_oracle.filt_decimate(oracle_lib.bold_sim(E, 0.04), 10, 100, 0.04)
+        assert np.max(np.abs(bold_oracle.fc(bold) - out["fc"][k])) < 1e-6                           # (b)
+        g = np.array([bold_oracle.get_all_metrics(out["fc"][k], emp[j]) for j in range(2)])
+        assert np.allclose(g, out["gof"][k], atol=1e-9)
+        assert abs(out["mean"][k] - out["fc"][k].mean()) < 1e-12
+        sync, meta = bold_oracle.kuramoto(bold)
+        assert abs(out["sync"][k] - sync) < 1e-6 and abs(out["meta"][k] - meta) < 1e-6
+    # (d) the same run in three slices, without the FC output: (c) NREM_SWEEP_FC_BATCH=33 makes finish() work in five batches
+    monkeypatch.setenv("NREM_SWEEP_FC_BATCH", "33")
+    plan2 = sweep.SweepPlan(p, B, n_maps=1, K=2, **kw)
+    plan2.begin(SC, G0, dG, s0, ds, streams, mG, mS, None)
+    left = plan2.chunks_total
+    while left > 0:
+        left = plan2.advance(3)
+    out2 = plan2.finish(emp)
+    for key in ("gof", "mean", "sync", "meta"):
+        assert np.array_equal(out[key], out2[key]), key
+    plan.close(); plan2.close()
 
 
 def test_large_connectome_persistent_cluster_mode_is_bit_identical(monkeypatch):
