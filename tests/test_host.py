@@ -184,9 +184,9 @@ def test_c_abi_argument_errors(built):
     p = ops.make_params(90, 1, 1, 20)
     one = C.c_void_p(8)                                        # a non-null dummy "device pointer": never dereferenced
     assert lib.nrem_fc_f64(None, 1, 10, 90, one, None) == -1 and b"null" in lib.nrem_last_error()
-    assert lib.nrem_fc_f64(one, 1, 10, 200, one, None) == -1 and b"N <= 128" in lib.nrem_last_error()
+    assert lib.nrem_fc_f64(one, 1, 10, 40000, one, None) == -1 and b"N <= 32768" in lib.nrem_last_error()
     assert lib.nrem_gof_f64(one, one, 1, 4, 3, 1.0, one, None, None) == -1
-    assert lib.nrem_gof_f64(one, one, 1, 4, 129, 1.0, one, None, None) == -1 and b"N <= 128" in lib.nrem_last_error()
+    assert lib.nrem_gof_f64(one, one, 1, 4, 40000, 1.0, one, None, None) == -1 and b"N <= 32768" in lib.nrem_last_error()
     assert lib.nrem_bold_sim_f64(one, 0, 10, 90, 0.04, one, None) == -1
     assert lib.nrem_wc_run_f64(None, one, one, one, None, None, 1, 1, 1, None, one, None) == -1
     assert lib.nrem_wc_run_f64(C.byref(p), one, one, one, None, one, 3, 5, 1, None, one, None) == -1      # noise_batch not in {1, B}
@@ -198,8 +198,13 @@ def test_c_abi_argument_errors(built):
     assert lib.nrem_filt_scratch_bytes(1, 40, 3, 20, 1) == -1      # fewer than 32 samples after the cut
     o = _lib.SweepOpts()
     plan = C.c_void_p()
+    pp = ops.make_params(9000, 1, 1, 20)
+    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"nnodes <= 8192" in lib.nrem_last_error()
     pp = ops.make_params(200, 1, 1, 20)
-    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"nnodes <= 128" in lib.nrem_last_error()
+    o.kernel, o.bold_downsamp = 5, 10                          # beyond 128 nodes only the large-connectome integrator (0 / 7) ...
+    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"large-connectome" in lib.nrem_last_error()
+    o.kernel = 0                                               # ... which takes one map pair per sweep
+    assert lib.nrem_sweep_create(C.byref(pp), C.byref(o), 4, 2, 4, C.byref(plan)) == -1 and b"one (mapG, mapS) pair" in lib.nrem_last_error()
     pw = ops.make_params(120, 1, 1, 20)
     o.kernel, o.bold_downsamp = 3, 10                          # the 128-simulation tcgen05 kernel is one 96-wide MMA tile
     assert lib.nrem_sweep_create(C.byref(pw), C.byref(o), 4, 1, 4, C.byref(plan)) == -1 and b"node-lane" in lib.nrem_last_error()
