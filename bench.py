@@ -279,8 +279,9 @@ def config5_leg(N=1000, B=4096, steps=40000):
                          "peak_note": "three BF16 passes at the tensor peak; " + src,
                          "executed_tflops": 3 * alg / us / 1e6,
                          "note": "round 2: the 3xBF16 split needs 1.5 TF32-pass equivalents (tcb: 2, tc3: 3), so the step got 18 % faster while the "
-                                 "executed-flop fraction stayed; the step is bound by phase 1 (state in L2/HBM: the 118 MB working set no longer "
-                                 "fits the L2) and the operand ring, see profiles/r02_big_connectome.md",
+                                 "executed-flop fraction stayed; with the FP32 plane of E in place and a_base as bf16 (working set 124 -> 93 MB) another 10 %.  "
+                                 "The step is bound by the operand ring and phase 1 alike (a third of the state / operand reads still miss the L2), "
+                                 "see profiles/r02_big_connectome.md",
                          "kernel": "wc_big_step_kernel<5, ., ., 0, 1>", "profile": "profiles/r02_big_connectome.md"}}
 
 
