@@ -254,8 +254,17 @@ __global__ void filt_backward_kernel(FiltCoef f, FiltScratch S, int64_t nslots, 
 
 // Sweep path: consume `rows` float32 E samples [rows][N][Bs] (simulation fastest) of the simulations
 // [sim0, sim0 + nsim), advance the Balloon-Windkessel state and the forward filter.  slot = node*Bs + sim.
+// Occupancy: the per-sample recursions are one dependent chain per thread (~460 clk per sample), so the kernel lives on resident
+// warps.  64 registers (8 CTAs per SM, a 4-deep load prefetch; 16 bytes of spill) instead of 90 (5 CTAs, 8-deep): +2.6 % on the whole
+// sweep (profiles/r02_kernel_variants.md).
+#ifndef NREM_K2_MINB
+#define NREM_K2_MINB 8
+#endif
+#ifndef NREM_K2_PF
+#define NREM_K2_PF 4
+#endif
 template <typename BT>
-__global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t row_base, int N, int64_t Bs, int64_t sim0, int64_t nsim,
+__global__ void __launch_bounds__(128, NREM_K2_MINB) bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t row_base, int N, int64_t Bs, int64_t sim0, int64_t nsim,
                                          int64_t Neq, BT dt, BT* bw_state /*[4][nth]*/, FiltCoef f, FiltScratch S, float* wring, int wL) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)N * nsim) return;
@@ -282,7 +291,7 @@ __global__ void bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t ro
     // The recursions below are sequential in the sample index, the LOADS are not: without the explicit block prefetch every sample
     // pays one HBM/L2 round trip (250 samples x ~0.8 us made this kernel 5.6 % of a sweep).  Block b + 1 is requested while block b
     // is processed.
-    constexpr int PF = 8;
+    constexpr int PF = NREM_K2_PF;
     float xnext[PF];
 #pragma unroll
     for (int j = 0; j < PF; ++j) xnext[j] = j < rows ? __ldcs(in + (int64_t)j * stride) : 0.f;

@@ -367,6 +367,11 @@ struct nrem_sweep_plan {
     std::vector<cudaStream_t> gstreams;
     std::vector<cudaEvent_t> gjoin;
     cudaEvent_t gfork;
+    // BOLD / filter launches run on their own high-priority stream per group, one chunk behind the integrator (the E samples go
+    // through a two-chunk ring): K1(c + 1) starts as soon as K1(c) ends instead of waiting for K2(c)
+    std::vector<cudaStream_t> kstreams;
+    std::vector<cudaEvent_t> k1done, k2done, kjoin;       // [group][buffer parity]; kjoin [group]
+    bool overlap_k2;
     // optional timing: (begin, end) event pairs around every API call on the caller's stream and around every
     // integrator launch of tile group 0
     bool prof_on;
@@ -668,7 +673,11 @@ int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, 
     P->nth = (int64_t)P->N * P->Bs;
     P->chunk_samples = o->chunk_samples > 0 ? o->chunk_samples : 250;
     if (int rc = prepare_filter(o->b, o->a, P->Tf, o->bold_downsamp, P->fh)) { delete P->big; delete P; return rc; }
-    P->ring_rows = P->chunk_samples; P->welch_nseg = 0; P->welchP = nullptr; P->welch.L = 0; P->wring = nullptr;
+    {
+        const char* e = getenv("NREM_K2_OVERLAP");             // 1 (default): BOLD / filter of chunk c overlaps the integration of chunk c + 1
+        P->overlap_k2 = e ? atoi(e) != 0 : true;
+    }
+    P->ring_rows = (P->overlap_k2 ? 2 : 1) * (int64_t)P->chunk_samples; P->welch_nseg = 0; P->welchP = nullptr; P->welch.L = 0; P->wring = nullptr;
     std::vector<float> h_win;
     std::vector<float2> h_tw, h_tw2;
     if (o->welch_nperseg > 0) {
@@ -764,7 +773,11 @@ int nrem_sweep_destroy(nrem_sweep_plan* plan) {
     for (cudaEvent_t e : plan->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : plan->span_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : plan->gjoin) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->k1done) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->k2done) cudaEventDestroy(e);
+    for (cudaEvent_t e : plan->kjoin) cudaEventDestroy(e);
     for (cudaStream_t g : plan->gstreams) cudaStreamDestroy(g);
+    for (cudaStream_t g : plan->kstreams) cudaStreamDestroy(g);
     if (plan->gfork) cudaEventDestroy(plan->gfork);
     delete plan->big;
     delete plan;
@@ -831,8 +844,26 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
     NREM_CUDA(cudaGetDevice(&dev));
     NREM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int ngroups = 1;
-    if (plan && tiles > sms) ngroups = (int)std::min<int64_t>((tiles + 7) / 8, 30);
+    const bool overlap = plan && plan->overlap_k2 && !Ebuf_all;
+    // every group needs a hardware queue for its integrator stream and, with overlap, one for its BOLD / filter stream (32 in all)
+    if (plan && tiles > sms) ngroups = (int)std::min<int64_t>((tiles + 7) / 8, overlap ? 15 : 30);
     if (plan) plan->last_groups = ngroups;
+    if (overlap) {
+        int lo = 0, hi = 0;
+        NREM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        while ((int)plan->kstreams.size() < ngroups) {
+            cudaStream_t k; cudaEvent_t e;
+            NREM_CUDA(cudaStreamCreateWithPriority(&k, cudaStreamNonBlocking, hi));
+            plan->kstreams.push_back(k);
+            for (int q = 0; q < 2; ++q) {
+                NREM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); plan->k1done.push_back(e);
+                NREM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); plan->k2done.push_back(e);
+            }
+            NREM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); plan->kjoin.push_back(e);
+        }
+    }
+    std::vector<char> k2pending((size_t)ngroups * 2, 0);      // a BOLD / filter launch of this call still reads buffer [g][parity]
+    bool k2used = false;
     std::vector<cudaStream_t> gs(1, st);
     if (ngroups > 1) {
         while ((int)plan->gstreams.size() < ngroups) {
@@ -876,11 +907,25 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
                 plan->ev_used += 2;
                 NREM_CUDA(cudaEventRecord(e0, gs[g]));
             }
+            const int par = (int)((row_base / chunk_samples) & 1);          // which half of the two-chunk ring this chunk writes
+            if (overlap && ph == 2 && k2pending[(size_t)g * 2 + par])       // the BOLD / filter launch of chunk c - 2 has left this half
+                NREM_CUDA(cudaStreamWaitEvent(gs[g], plan->k2done[(size_t)g * 2 + par], 0));
             if (int rc = launch_integrator(kernel, A, t1 - t0, gs[g])) return rc;
             if (e1) NREM_CUDA(cudaEventRecord(e1, gs[g]));
             if (ph == 2 && plan) {
                 const float* Echunk = d.Ebuf + ring_row0 * (int64_t)plan->N * Bs;
-                if (int rc = launch_bold_chunk(plan, Echunk, rows, row_base, t0 * tsz, (t1 - t0) * tsz, gs[g])) return rc;
+                cudaStream_t ks = gs[g];
+                if (overlap) {
+                    ks = plan->kstreams[g];
+                    NREM_CUDA(cudaEventRecord(plan->k1done[(size_t)g * 2 + par], gs[g]));
+                    NREM_CUDA(cudaStreamWaitEvent(ks, plan->k1done[(size_t)g * 2 + par], 0));
+                }
+                if (int rc = launch_bold_chunk(plan, Echunk, rows, row_base, t0 * tsz, (t1 - t0) * tsz, ks)) return rc;
+                if (overlap) {
+                    NREM_CUDA(cudaEventRecord(plan->k2done[(size_t)g * 2 + par], ks));
+                    k2pending[(size_t)g * 2 + par] = 1;
+                    k2used = true;
+                }
             }
         }
         cur.i0 += n; cur.step += n; cur.first = 0;
@@ -891,6 +936,12 @@ static int integrate(const nrem_wc_params& p, int kernel, const StagePtrs& d, in
         for (int g = 0; g < ngroups; ++g) {
             NREM_CUDA(cudaEventRecord(plan->gjoin[g], gs[g]));
             NREM_CUDA(cudaStreamWaitEvent(st, plan->gjoin[g], 0));
+        }
+    }
+    if (k2used) {            // the caller's stream continues (next slice, nrem_sweep_finish) after the last BOLD / filter launches
+        for (int g = 0; g < ngroups; ++g) {
+            NREM_CUDA(cudaEventRecord(plan->kjoin[g], plan->kstreams[g]));
+            NREM_CUDA(cudaStreamWaitEvent(st, plan->kjoin[g], 0));
         }
     }
     return NREM_OK;

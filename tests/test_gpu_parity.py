@@ -413,9 +413,10 @@ def test_sliced_run_equals_one_call(aal90):
     plan.close()
 
 
-def test_sweep_with_more_tiles_than_sms(aal90):
+def test_sweep_with_more_tiles_than_sms(aal90, monkeypatch):
     """More 128-tiles than SMs switches the host scheduler to independent tile-group streams; the results must
-    not depend on it (same simulations in a small single-stream batch give identical numbers)."""
+    not depend on it (same simulations in a small single-stream batch give identical numbers), nor on whether the BOLD / filter
+    launches run one chunk behind the integrator on their own streams (NREM_K2_OVERLAP, the default) or in line."""
     import torch
     from nremmodfc_b200 import ops, sweep
     sms = torch.cuda.get_device_properties(0).multi_processor_count
@@ -431,6 +432,13 @@ def test_sweep_with_more_tiles_than_sms(aal90):
     big = plan.run(aal90["SC"], emp, np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams)
     assert plan.profile()["tile_groups"] > 1
     plan.close()
+    monkeypatch.setenv("NREM_K2_OVERLAP", "0")
+    plan = sweep.SweepPlan(p, B, **kw)
+    inline = plan.run(aal90["SC"], emp, np.full(B, 0.16), dG, np.full(B, 7.68), ds, streams)
+    plan.close()
+    monkeypatch.delenv("NREM_K2_OVERLAP")
+    for key in ("gof", "mean", "sync", "meta"):
+        assert np.array_equal(big[key], inline[key]), key
     pick = np.r_[0:40, B - 300:B]
     small = sweep.sweep_gof(p, aal90["SC"], emp, np.full(len(pick), 0.16), dG[pick], np.full(len(pick), 7.68), ds[pick], streams[pick], **kw)
     assert np.isfinite(big["gof"]).all()
