@@ -263,7 +263,9 @@ __global__ void filt_backward_kernel(FiltCoef f, FiltScratch S, int64_t nslots, 
 #ifndef NREM_K2_PF
 #define NREM_K2_PF 4
 #endif
-template <typename BT>
+// STEADY (decided by the host, launch_bold_chunk): the whole chunk lies strictly inside the filtered signal (no cut, no odd extension,
+// not the end), so the per-sample code has no position checks; WR: also write the series-major sample ring of the Welch kernel.
+template <typename BT, bool STEADY, bool WR>
 __global__ void __launch_bounds__(128, NREM_K2_MINB) bold_filter_chunk_kernel(const float* Ebuf, int rows, int64_t row_base, int N, int64_t Bs, int64_t sim0, int64_t nsim,
                                          int64_t Neq, BT dt, BT* bw_state /*[4][nth]*/, FiltCoef f, FiltScratch S, float* wring, int wL) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,13 +282,10 @@ __global__ void __launch_bounds__(128, NREM_K2_MINB) bold_filter_chunk_kernel(co
     const float* in = Ebuf + slot;
     const int64_t stride = (int64_t)N * Bs;
     // optional series-major copy of the samples for the Welch kernel: wring[slot][sample mod wL], 16-byte stores
-    float* wr = wring ? wring + slot * (int64_t)wL : nullptr;
+    float* wr = WR ? wring + slot * (int64_t)wL : nullptr;
     const int lead = (int)((4 - (row_base & 3)) & 3), full_end = lead + ((rows - lead) & ~3);
-    int wpos = wr ? (int)(row_base % wL) : 0;                       // ring position of the current sample
+    int wpos = WR ? (int)(row_base % wL) : 0;                       // ring position of the current sample
     float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-    // whole chunk strictly inside the filtered signal (no cut, no odd extension, not the end)?  -> lean loop
-    const int64_t n0 = row_base - Neq;
-    const bool steady = n0 >= 16 && n0 + rows <= f.Tf - 16;
     const int ds = (int)f.ds, Jm1 = (int)f.J - 1;
     // The recursions below are sequential in the sample index, the LOADS are not: without the explicit block prefetch every sample
     // pays one HBM/L2 round trip (250 samples x ~0.8 us made this kernel 5.6 % of a sweep).  Block b + 1 is requested while block b
@@ -306,7 +305,7 @@ __global__ void __launch_bounds__(128, NREM_K2_MINB) bold_filter_chunk_kernel(co
         const int rr = r0 + j;
         if (rr >= rows) break;
         const float xe = xcur[j];
-        if (wr) {
+        if (WR) {
             if (rr < lead || rr >= full_end) wr[wpos] = xe;
             else {
                 const int ph = (rr - lead) & 3;
@@ -316,7 +315,7 @@ __global__ void __launch_bounds__(128, NREM_K2_MINB) bold_filter_chunk_kernel(co
             if (++wpos == wL) wpos = 0;
         }
         const double y = bw.step((BT)xe, dt);
-        if (steady) {
+        if (STEADY) {
             filt_push_steady(r, f, S, slot, y, ds, Jm1);
         } else {
             const int64_t ts = row_base + rr;

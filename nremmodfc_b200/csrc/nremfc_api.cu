@@ -799,12 +799,24 @@ static int launch_bold_chunk(nrem_sweep_plan* plan, const float* Echunk, int row
                              cudaStream_t st) {
     const unsigned blocks = (unsigned)((plan->N * nsim + 127) / 128);
     const int64_t Bs = plan->Bs;
-    if (plan->o.bold_f32)
-        bold_filter_chunk_kernel<float><<<blocks, 128, 0, st>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
-                                                               (float)plan->o.bold_dt, (float*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
-    else
-        bold_filter_chunk_kernel<double><<<blocks, 128, 0, st>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq,
-                                                                plan->o.bold_dt, (double*)plan->bw_state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
+    // whole chunk strictly inside the filtered signal (no cut, no odd extension, not the end)?  -> the lean kernel
+    const int64_t n0 = row_base - plan->o.Neq;
+    const bool steady = n0 >= 16 && n0 + rows <= plan->fh.f.Tf - 16;
+    const bool wr = plan->wring != nullptr;
+    auto launch = [&](auto kern, auto dt, auto* state) {
+        kern<<<blocks, 128, 0, st>>>(Echunk, rows, row_base, plan->N, Bs, sim0, nsim, plan->o.Neq, dt, state, plan->fh.f, plan->S, plan->wring, plan->welch.L);
+    };
+    if (plan->o.bold_f32) {
+        float* state = (float*)plan->bw_state;
+        const float dt = (float)plan->o.bold_dt;
+        if (steady) { if (wr) launch(bold_filter_chunk_kernel<float, true, true>, dt, state); else launch(bold_filter_chunk_kernel<float, true, false>, dt, state); }
+        else { if (wr) launch(bold_filter_chunk_kernel<float, false, true>, dt, state); else launch(bold_filter_chunk_kernel<float, false, false>, dt, state); }
+    } else {
+        double* state = (double*)plan->bw_state;
+        const double dt = plan->o.bold_dt;
+        if (steady) { if (wr) launch(bold_filter_chunk_kernel<double, true, true>, dt, state); else launch(bold_filter_chunk_kernel<double, true, false>, dt, state); }
+        else { if (wr) launch(bold_filter_chunk_kernel<double, false, true>, dt, state); else launch(bold_filter_chunk_kernel<double, false, false>, dt, state); }
+    }
     NREM_LAUNCHED();
     // Welch: a segment [e - L, e) is complete whenever e >= L and (e - L) is a multiple of the hop L/2
     const int64_t e_row = row_base + rows;
