@@ -300,6 +300,31 @@ __global__ void __launch_bounds__(128, NREM_K2_MINB) bold_filter_chunk_kernel(co
       for (int j = 0; j < PF; ++j) xcur[j] = xnext[j];
 #pragma unroll
       for (int j = 0; j < PF; ++j) xnext[j] = r0 + PF + j < rows ? __ldcs(in + (int64_t)(r0 + PF + j) * stride) : 0.f;
+      // Lean block: none of the PF samples writes a decimated output, starts or ends a summary chunk (the counters are the same in
+      // every thread, so this is one uniform branch per block; with ds = 1000 all but one or two blocks of a launch are lean).  Same
+      // arithmetic in the same order as filt_push_steady.
+      if (STEADY && !WR && r0 + PF <= rows && r.kd >= 1 && r.kd + PF <= ds && r.k >= 1 && (r.k + PF < ds || r.j >= Jm1)) {
+        const double2* pt = reinterpret_cast<const double2*>(f.ptab) + 2 * r.k;
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const double u = bw.step((BT)xcur[j], dt);
+            const double w = f.b0 * u + 2.0 * ((f.Rr[0] * r.s[0] - f.Ri[0] * r.s[1]) + (f.Rr[1] * r.s[2] - f.Ri[1] * r.s[3]));
+            const double a0 = f.Pr[0] * r.s[0] - f.Pi[0] * r.s[1] + u;
+            const double a1 = f.Pr[0] * r.s[1] + f.Pi[0] * r.s[0];
+            const double a2 = f.Pr[1] * r.s[2] - f.Pi[1] * r.s[3] + u;
+            const double a3 = f.Pr[1] * r.s[3] + f.Pi[1] * r.s[2];
+            r.s[0] = a0; r.s[1] = a1; r.s[2] = a2; r.s[3] = a3;
+            const double2 p01 = __ldg(pt + 2 * j), p23 = __ldg(pt + 2 * j + 1);
+            r.c[0] = fma(p01.x, w, r.c[0]);
+            r.c[1] = fma(p01.y, w, r.c[1]);
+            r.c[2] = fma(p23.x, w, r.c[2]);
+            r.c[3] = fma(p23.y, w, r.c[3]);
+        }
+        r.k += PF;
+        r.kd += PF;
+        if (r.kd == ds) { r.kd = 0; ++r.jd; }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < PF; ++j) {
         const int rr = r0 + j;
