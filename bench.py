@@ -278,6 +278,10 @@ def config5_leg(N=1000, B=4096, steps=40000):
                          "peak": alg / ideal_us / 1e6, "frac": ideal_us / us, "traffic": None,
                          "peak_note": "three BF16 passes at the tensor peak; " + src,
                          "executed_tflops": 3 * alg / us / 1e6,
+                         "frac_round1_definition": (alg / (bf16 / 2 * 1e12) * 1e6 + 2 * alg / (bf16 * 1e12) * 1e6) / us,
+                         "frac_round1_definition_note": "ideal time of the PREVIOUS kernel's pass mix (1 TF32 + 2 BF16 passes, tcb) over this run's time: "
+                                                        "comparable with the 0.53 / 0.58 of round 1 / the first half of round 2; frac itself charges only the "
+                                                        "three BF16 passes this kernel executes",
                          "note": "round 2: the 3xBF16 split needs 1.5 TF32-pass equivalents (tcb: 2, tc3: 3), so the step got 18 % faster while the "
                                  "executed-flop fraction stayed; with the FP32 plane of E in place and a_base as bf16 (working set 124 -> 93 MB) another 10 %.  "
                                  "The step is bound by the operand ring and phase 1 alike (a third of the state / operand reads still miss the L2), "
