@@ -289,6 +289,26 @@ def config5_leg(N=1000, B=4096, steps=40000):
                          "kernel": "wc_big_step_kernel<5, ., ., 0, 1>", "profile": "profiles/r02_big_connectome.md"}}
 
 
+def k1_only_leg(d, steps=20000):
+    """The integrator kernel alone on one full wave (one 128-simulation tile per SM, `steps` Euler steps in one launch chain, CUDA events):
+    SM cycles per Euler step of a tile without the BOLD / filter launches and the tile-group scheduling of the sweep -- the denominator of the
+    kernel's own composite-bound fraction."""
+    import torch
+    from nremmodfc_b200 import ops
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = sms * 128
+    rng = np.random.default_rng(0)
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    p = ops.make_params(90, 0, steps, 0, P=0.4, rhoE=0.18, seed=1)
+    ms = []
+    for _ in range(3):          # first call warms up
+        ops.integrate_f32(p, d["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), ds, kernel="tc3", record=False)
+        ms.append(ops.last_integrate_ms())
+    best = min(ms[1:])
+    return {"tiles": sms, "euler_steps": steps, "ms": best, "us_per_euler_step": best * 1e3 / steps,
+            "sims_per_s_equivalent": B * steps / (best * 1e-3) / 1.001e7}
+
+
 def config1_leg(d, SC, emp):
     """BASELINE configs[0]: ONE full-length run (AAL90, G = 0.16, sigma = 7.68, one seed) through the drop-in module surface, exactly the
     reference's call sequence (cortex_run.py:103-116 / whole_sweep_both.py:66-96): attributes, run.recompile(), run() -> Y_t float64
@@ -545,6 +565,13 @@ def run_ours(args):
         if world == 1 and not strong:
             if not args.no_modalities:
                 line["modalities"] = [modality_leg(args, d, SC, emp, w) for w in ("map", "shuffled")]
+            if lim and args.kernel in ("auto", "tc3"):
+                k1 = k1_only_leg(d)
+                k1["clk_per_tile_step"] = k1["us_per_euler_step"] * sm_mhz
+                k1["composite_frac"] = floors[binding] / k1["clk_per_tile_step"]
+                k1["note"] = ("the integrator alone on one full wave: the kernel's own fraction of its composite (" + binding + ") bound; "
+                              "`composite.frac` above is the same floor over the whole sweep's device time")
+                roof["composite"]["kernel_only"] = k1
             if not args.no_config5:
                 line["config5"] = config5_leg()
             if not args.no_config1:
