@@ -569,6 +569,12 @@ def run_ours(args):
                 k1 = k1_only_leg(d)
                 k1["clk_per_tile_step"] = k1["us_per_euler_step"] * sm_mhz
                 k1["composite_frac"] = floors[binding] / k1["clk_per_tile_step"]
+                if lim.get("sm_mhz_in_capture"):
+                    # the cycle counter of the ncu capture of this kernel ran at sm_mhz_in_capture while nvidia-smi showed sm_mhz: cycles are
+                    # wall time x the ACTUAL clock, so this is the figure comparable with frac_of_composite_bound_under_ncu
+                    k1["sm_mhz_in_ncu_capture"] = lim["sm_mhz_in_capture"]
+                    k1["clk_per_tile_step_at_capture_clock"] = k1["us_per_euler_step"] * lim["sm_mhz_in_capture"]
+                    k1["composite_frac_at_capture_clock"] = floors[binding] / k1["clk_per_tile_step_at_capture_clock"]
                 k1["note"] = ("the integrator alone on one full wave: the kernel's own fraction of its composite (" + binding + ") bound; "
                               "`composite.frac` above is the same floor over the whole sweep's device time")
                 roof["composite"]["kernel_only"] = k1

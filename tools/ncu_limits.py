@@ -62,6 +62,9 @@ out = {
     "gpu_time_ms": num("gpu__time_duration.sum") * (1e-3 if M["gpu__time_duration.sum"][1].lower().startswith("us") else
                                                     1e-6 if M["gpu__time_duration.sum"][1].lower().startswith("ns") else 1.0),
     "clk_per_tile_step_ncu": clk_step,
+    # SM clock the kernel actually ran at in the capture (cycle counter over wall time; --clock-control none): lower than the
+    # clocks.sm figure nvidia-smi reports while this kernel runs
+    "sm_mhz_in_capture": None,
     "warp_instructions_per_tile_step": num("smsp__inst_executed.sum") / (tiles * steps),
     "registers_per_thread": num("launch__registers_per_thread"),
     "pipe_busy_pct": pct,
@@ -70,6 +73,7 @@ out = {
     "frac_of_composite_bound_under_ncu": max(floors.values()) / clk_step,
     "dram_bytes_per_launch": dram,
 }
+out["sm_mhz_in_capture"] = cyc / (out["gpu_time_ms"] * 1e-3) / 1e6
 with open(os.path.join(ROOT, "profiles", "k1_limits.json"), "w") as fh:
     json.dump(out, fh, indent=1)
 
