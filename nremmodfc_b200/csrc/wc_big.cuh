@@ -3,11 +3,11 @@
 // Replaces wilsonCowan()+run() (netwWilsonCowanPlastic.py:77-137) when the nodes of a simulation no longer fit the
 // registers of one CTA.  Per step the coupling of ALL simulations is one GEMM
 //     D[Bs sims, N nodes] = E[Bs, N] x SC^T[N, N]            (2 Bs N^2 flop: 8.2 GFLOP at Bs = 4096, N = 1000)
-// tiled 128 sims x 256 nodes per CTA: a producer thread streams K-slices of both operands from L2 into a 4-stage
-// shared-memory ring with cp.async.bulk (mbarrier complete_tx), one thread issues tcgen05.mma (kind::tf32, M = 128,
-// N = 256, K = 8; 3xTF32 split as in wc_tc.cuh) into a 128 x 256 FP32 accumulator in TMEM, and the epilogue warps fuse
-// the whole node update (Philox noise, both sigmoids, E/I/a_ie Euler step, recording) onto the accumulator, so the
-// coupling never touches memory.
+// tiled 128 sims x 256 nodes per CTA (two such tiles per CTA pair: cta_group::2, M = 256): a producer thread streams K-slices
+// of both operands from L2 into a shared-memory ring (4 to 14 stages, by mode) with cp.async.bulk (mbarrier complete_tx), one
+// thread issues tcgen05.mma (kind::tf32 / kind::f16, N = 256; split precision, see the modes below) into a 128 x 256 FP32
+// accumulator in TMEM, and the epilogue warps fuse the whole node update (Philox noise, both sigmoids, E/I/a_ie Euler step,
+// recording) onto the accumulator, so the coupling never touches memory.  The default mode is 5 ("bf3").
 //
 // HBM/L2 layout: every operand lives in global memory as the exact shared-memory image the tensor core wants (no-swizzle
 // K-major canonical layout, [k/4][row][4] floats), so a pipeline stage is ONE contiguous bulk copy per operand:
@@ -18,7 +18,7 @@
 //   I, a_base, a_delta                               [tile][KG][128][4], updated in place (one owner thread per element)
 // KG = ceil(N/16)*4 four-node groups; padding nodes are zero in every image and are never written.
 //
-// Three precisions of the contraction (template MODE):
+// Four precisions of the contraction (template MODE):
 //   1 "tc"   one TF32 pass (operands truncated to TF32 by the tensor core)
 //   3 "tc3"  3xTF32: Eh.Sh + El.Sh + Eh.Sl with FP32 residuals (El = E - Eh), 6 TF32 MMAs per 16 input nodes
 //   4 "tcb"  TF32 main pass on the raw FP32 operands (the tensor core ignores the low 13 mantissa bits: Eh = trunc(E)) plus
