@@ -614,7 +614,7 @@ def main():
     ap.add_argument("--no-modalities", action="store_true", help="skip the map / shuffled-map sweeps (configs[2], configs[3])")
     args = ap.parse_args()
     if args.cpu_frac is None:
-        args.cpu_frac = 0.1
+        args.cpu_frac = 0.15          # >= 10 s of wall per sample on a 16-core box
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on communicator
     # creation), so everything but our own print() goes to stderr: fd 1 is pointed at fd 2 and sys.stdout keeps the real one.
     sys.stdout.flush()
