@@ -145,7 +145,7 @@ typedef struct nrem_sweep_opts {
 
 /* 7 <= nnodes <= 8192.  Up to 128 nodes the register-resident integrators (kernels 1-6) run; above that (any other parcellation,
  * BASELINE configs[4]) the plan integrates with the large-connectome kernel of nrem_big_integrate_f32 and runs the same
- * BOLD -> filter -> FC -> GoF -> Kuramoto chain, FC / GoF in batches of simulations (n_maps must be 1, no per-node tables). */
+ * BOLD -> filter -> FC -> GoF -> Kuramoto chain, FC / GoF in batches of simulations (n_maps must be 1).                    */
 int nrem_sweep_create(const nrem_wc_params* p, const nrem_sweep_opts* o, int B, int n_maps, int K,
                       nrem_sweep_plan** plan);
 int nrem_sweep_destroy(nrem_sweep_plan* plan);
@@ -230,6 +230,12 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
                            const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                            const uint64_t* streams, int B, int64_t nrec, float* E_samples, float* final_state,
                            float* coup_first, void* stream);
+/* Same with every node parameter as a per-node vector (netwWilsonCowanPlastic.py:21): node_params = NULL or device
+ * [NREM_NODE_PARAMS, N] in the order of nrem_wc_run_f64_ex; kernel 0 / 7 (bf3) only.                                  */
+int nrem_big_integrate_f32_ex(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG, const double* mapS,
+                              const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                              const uint64_t* streams, const double* node_params, int B, int64_t nrec, float* E_samples,
+                              float* final_state, float* coup_first, void* stream);
 
 /* Self-test of the tcgen05 contraction used by kernels 2/3: out[128,96] = E[128,96] x SCp[96,96]^T (float32,
  * device pointers).  passes = 1 (TF32) or 3 (3xTF32).  The shared-memory descriptor fields (bytes) and the

@@ -16,7 +16,7 @@ ABI_SYMBOLS = [
     "nrem_bold_sim_f64", "nrem_filt_scratch_bytes", "nrem_filtfilt_decimate_f64", "nrem_fc_f64", "nrem_gof_f64", "nrem_kuramoto_f64",
     "nrem_sweep_create", "nrem_sweep_destroy", "nrem_sweep_device_bytes", "nrem_sweep_run",
     "nrem_sweep_set_node_params", "nrem_sweep_kernel", "nrem_sweep_begin", "nrem_sweep_chunks_total", "nrem_sweep_advance", "nrem_sweep_finish", "nrem_sweep_feed_samples",
-    "nrem_sweep_integrate_f32", "nrem_sweep_integrate_f32_ex", "nrem_big_integrate_f32", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
+    "nrem_sweep_integrate_f32", "nrem_sweep_integrate_f32_ex", "nrem_big_integrate_f32", "nrem_big_integrate_f32_ex", "nrem_launch_count", "nrem_selftest_tc_coupling", "nrem_measure_fma_peak", "nrem_last_integrate_ms", "nrem_sweep_set_profiling", "nrem_sweep_get_profile",
 ]
 
 
@@ -75,6 +75,7 @@ lib.nrem_sweep_advance.argtypes = [_vp, _i64, C.POINTER(_i64), _vp]
 lib.nrem_sweep_finish.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
 lib.nrem_sweep_feed_samples.argtypes = [_vp, _vp, _i64, _vp]
 lib.nrem_big_integrate_f32.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 8 + [_i, _i64, _vp, _vp, _vp, _vp]
+lib.nrem_big_integrate_f32_ex.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 9 + [_i, _i64, _vp, _vp, _vp, _vp]
 lib.nrem_sweep_integrate_f32.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 7 + [C.POINTER(C.c_int32), _vp, _i, _i, _i64, _vp, _vp, _vp]
 lib.nrem_sweep_integrate_f32_ex.argtypes = [C.POINTER(WCParams), _i] + [_vp] * 7 + [C.POINTER(C.c_int32), _vp, _vp, _i, _i, _i64, _vp, _vp, _vp]
 lib.nrem_measure_fma_peak.argtypes = [C.POINTER(_d), C.POINTER(_d)]

@@ -398,7 +398,7 @@ struct BigRun {
     bool pair = false, pdl = true, want_persist = false;
     int64_t Bs = 0, bytes = 0;
     size_t nf4 = 0;
-    int64_t o_a0 = 0, o_a1 = 0, o_i = 0, o_ab = 0, o_ad = 0, o_b = 0, o_par = 0, o_st = 0, o_mg = 0, o_ms = 0;
+    int64_t o_a0 = 0, o_a1 = 0, o_i = 0, o_ab = 0, o_ad = 0, o_b = 0, o_par = 0, o_st = 0, o_mg = 0, o_ms = 0, o_np = 0;
     char* base = nullptr;
     float4* img[2] = {nullptr, nullptr};
     BigArgs A;
@@ -432,6 +432,7 @@ static int big_layout(BigRun& R, const nrem_wc_params& p, int kernel, int B) {
     R.o_i = take(16 * (int64_t)R.nf4); R.o_ab = take(16 * (int64_t)R.nf4); R.o_ad = take(16 * (int64_t)R.nf4);
     R.o_b = take(2 * 16 * (int64_t)R.slices * R.KG * kBigNT);
     R.o_par = take(4 * 4 * R.Bs); R.o_st = take(8 * R.Bs); R.o_mg = take(4 * R.Kpad); R.o_ms = take(4 * R.Kpad);
+    R.o_np = take(4 * (int64_t)kBigNpar * R.Kpad);
     R.bytes = off;
     const char* env_pdl = getenv("NREM_BIG_PDL");
     R.pdl = env_pdl ? atoi(env_pdl) != 0 : true;
@@ -440,9 +441,12 @@ static int big_layout(BigRun& R, const nrem_wc_params& p, int kernel, int B) {
 
 // Stages SC, the maps, the per-simulation parameters and the initial condition into R.base (R.bytes of device memory) and prepares
 // the kernel arguments.  homo: 1 = no per-node maps (scalar G, sigma per simulation), 0 = maps.
+//   node_params: NULL or device [NREM_NODE_PARAMS, N] (every node parameter as a per-node vector; bf3 kernel, one launch per step)
 static int big_stage(BigRun& R, const nrem_wc_params& p, void* dev, const double* CM, const double* mapG, const double* mapS,
                      const double* G0, const double* dG, const double* sigma0, const double* dsigma, const uint64_t* streams,
-                     int B, int homo, cudaStream_t st) {
+                     int B, int homo, cudaStream_t st, const double* node_params = nullptr) {
+    NREM_REQUIRE(!node_params || (R.k == 7 && !R.want_persist), "per-node parameter tables need the bf3 kernel with one launch per step");
+    if (node_params) homo = 0;                  // the table kernels are instantiated for the map form (maps of ones are exact)
     R.base = (char*)dev;
     char* base = R.base;
     const int N = R.N, KG = R.KG, slices = R.slices;
@@ -457,8 +461,14 @@ static int big_stage(BigRun& R, const nrem_wc_params& p, void* dev, const double
     NREM_LAUNCHED();
     BigArgs& A = R.A;
     A.c = make_const(p);
+    A.npar = nullptr;
+    if (node_params) {
+        big_stage_npar_kernel<<<(R.Kpad + 255) / 256, 256, 0, st>>>(node_params, N, R.Kpad, p.dtSim, (float*)(base + R.o_np));
+        NREM_LAUNCHED();
+        A.npar = (const float4*)(base + R.o_np);
+    }
     big_init_kernel<<<(unsigned)((R.nf4 + 255) / 256), 256, 0, st>>>(A.c, (int64_t)R.nf4, KG, R.mixed, (float4*)(base + R.o_a0), R.nf4, (float4*)(base + R.o_i),
-                                                                    (float4*)(base + R.o_ab), (float4*)(base + R.o_ad));
+                                                                    (float4*)(base + R.o_ab), (float4*)(base + R.o_ad), (const float*)A.npar);
     NREM_LAUNCHED();
     R.img[0] = (float4*)(base + R.o_a0); R.img[1] = (float4*)(base + R.o_a1);
     A.Bimg = (const float4*)(base + R.o_b);
@@ -491,6 +501,9 @@ static int big_stage(BigRun& R, const nrem_wc_params& p, void* dev, const double
     R.grid = R.pair ? dim3((unsigned)R.tiles, (unsigned)slices) : dim3((unsigned)slices, (unsigned)R.tiles);
     R.kern_persist = pick2(std::integral_constant<int, 1>{});
     R.kern = R.pair ? pick2(std::integral_constant<int, 2>{}) : pick2(std::integral_constant<int, 0>{});
+    if (node_params)
+        R.kern = R.pair ? (fullN ? wc_big_step_kernel<5, true, false, false, true, true> : wc_big_step_kernel<5, false, false, false, true, true>)
+                        : (fullN ? wc_big_step_kernel<5, true, false, false, false, true> : wc_big_step_kernel<5, false, false, false, false, true>);
     NREM_CUDA(cudaFuncSetAttribute(R.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R.smem));
     return NREM_OK;
 }
@@ -1008,8 +1021,13 @@ static int big_advance(nrem_sweep_plan* P, int64_t max_chunks, cudaStream_t st) 
 
 int nrem_sweep_set_node_params(nrem_sweep_plan* P, const double* node_params, void* stream) {
     NREM_REQUIRE(P, "plan is null");
-    NREM_REQUIRE(P->kernel != 7 || !node_params, "per-node parameter tables are not available on the large-connectome integrator (more than 128 nodes)");
-    if (P->kernel == 7) return NREM_OK;
+    if (P->kernel == 7) {           // large-connectome integrator: the table is staged by nrem_sweep_begin
+        if (node_params)
+            NREM_CUDA(cudaMemcpyAsync(P->node_par, node_params, sizeof(double) * NREM_NODE_PARAMS * (size_t)P->N, cudaMemcpyDeviceToDevice,
+                                      (cudaStream_t)stream));
+        P->has_node_par = node_params != nullptr;
+        return NREM_OK;
+    }
     if (!node_params) { P->has_node_par = false; P->kernel = resolve_kernel(P->o.kernel, P->N, P->B, false); P->tile_sims = kernel_tile_sims(P->kernel); return NREM_OK; }
     NREM_REQUIRE(P->o.kernel == 0 || P->o.kernel >= 5, "per-node parameter tables need the node-lane kernel (kernel 0, 5 or 6)");
     NREM_CUDA(cudaMemcpyAsync(P->node_par, node_params, sizeof(double) * NREM_NODE_PARAMS * (size_t)P->N, cudaMemcpyDeviceToDevice,
@@ -1038,7 +1056,7 @@ int nrem_sweep_begin(nrem_sweep_plan* P, const double* CM, const double* mapG, c
         // homogeneous = -1 (unknown): the map kernel is used; it is exact for maps of ones, too
         P->homo = homogeneous == 1 ? 1 : 0;
         if (int rc = big_stage(*P->big, P->p, P->big_dev, CM, P->homo ? nullptr : mapG, P->homo ? nullptr : mapS, G0, dG, sigma0, dsigma, streams,
-                               P->B, P->homo, st)) return rc;
+                               P->B, P->homo, st, P->has_node_par ? P->node_par : nullptr)) return rc;
         P->cur = IntegCursor{0, 0, 0, 1};
         P->fed_rows = 0;
         P->begun = true;
@@ -1258,6 +1276,14 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
                            const double* G0, const double* dG, const double* sigma0, const double* dsigma,
                            const uint64_t* streams, int B, int64_t nrec, float* E_samples, float* final_state,
                            float* coup_first, void* stream) {
+    return nrem_big_integrate_f32_ex(p, kernel, CM, mapG, mapS, G0, dG, sigma0, dsigma, streams, nullptr, B, nrec, E_samples, final_state,
+                                     coup_first, stream);
+}
+
+int nrem_big_integrate_f32_ex(const nrem_wc_params* p, int kernel, const double* CM, const double* mapG, const double* mapS,
+                              const double* G0, const double* dG, const double* sigma0, const double* dsigma,
+                              const uint64_t* streams, const double* node_params, int B, int64_t nrec, float* E_samples,
+                              float* final_state, float* coup_first, void* stream) {
     if (int rc = check_params(p)) return rc;
     NREM_REQUIRE(CM && G0 && dG && sigma0 && dsigma && streams, "null array");
     NREM_REQUIRE(B >= 1, "bad shape");
@@ -1274,7 +1300,7 @@ int nrem_big_integrate_f32(const nrem_wc_params* p, int kernel, const double* CM
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     auto body = [&]() -> int {
-        if (int r = big_stage(R, *p, dev, CM, mapG, mapS, G0, dG, sigma0, dsigma, streams, B, (!mapG && !mapS) ? 1 : 0, st)) return r;
+        if (int r = big_stage(R, *p, dev, CM, mapG, mapS, G0, dG, sigma0, dsigma, streams, B, (!mapG && !mapS) ? 1 : 0, st, node_params)) return r;
         BigArgs& A = R.A;
         const int slices = R.slices, tiles = R.tiles;
         // NREM_BIG_DBG=<step>: phase timing of that Euler step (globaltimer stamps per CTA, printed to stderr) -- developer switch

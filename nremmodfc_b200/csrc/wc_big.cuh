@@ -125,6 +125,10 @@ __device__ __forceinline__ uint32_t bf16x2(float lo_elem, float hi_elem) {      
     return r;
 }
 
+// rows of the per-node table of the NODEPAR kernels ("Any of them can be redefined as a vector of length nnodes", netwWilsonCowanPlastic.py:21)
+enum { kNpAee = 0, kNpAei, kNpAii, kNpKE, kNpKI, kNpPmu, kNpRhoE, kNpRE, kNpRI, kNpNmu, kNpSigI2, kNpA0, kBigNpar };
+__device__ __forceinline__ float f4c(const float4& v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+
 struct BigArgs {
     BatchConst c;
     const float4* Acur;        // E(t) image
@@ -133,6 +137,7 @@ struct BigArgs {
     float4* I4;
     float4* ab4;               // a_ie base (bf3: bf16, addressed as uint2[])
     float4* Fst;               // bf3: the FP32 plane of E, updated in place by its owner thread (plane F of image 0)
+    const float4* npar;        // NODEPAR kernels: per-node parameter table [kBigNpar][Kpad] floats (big_stage_npar_kernel), else NULL
     float4* ad4;               // a_ie delta (a_ie = base + delta, see wc_tc.cuh)
     const float* par;          // [4][Bs]: G0, dG, sigma0, dsigm
     const uint64_t* streams;   // [Bs]
@@ -217,10 +222,12 @@ struct BigQuad {             // state of one thread's four-node group
 // PAIR   : launched as clusters (2, 1, 1) on a (tiles, slices) grid: tiles 2p and 2p+1 of a node slice form a CTA pair (cta_group::2).  Rank 0 issues the
 //          M = 256 MMAs for both; every CTA streams its own A tile and its half of the B tile; the peer relays "my stage has
 //          landed" to the leader's full barrier; tcgen05.commit multicasts the stage-free / accumulator-ready arrivals to both.
-template <int MODE, bool FULL, bool HOMO, bool PERSIST, bool PAIR = false>
+// NODEPAR: every node parameter from a per-node table (A.npar) instead of the scalars of the launch (bf3, one launch per step).
+template <int MODE, bool FULL, bool HOMO, bool PERSIST, bool PAIR = false, bool NODEPAR = false>
 __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigArgs A) {
     extern __shared__ __align__(128) unsigned char smraw[];
     static_assert(!(PAIR && PERSIST), "the CTA-pair kernel is launched once per Euler step");
+    static_assert(!NODEPAR || (MODE == 5 && !PERSIST && !HOMO), "per-node parameter tables: bf3, one launch per step, map kernel");
     constexpr bool SPLIT = MODE == 3;
     constexpr bool BF3 = MODE == 5;
     constexpr bool MIXED = MODE == 4 || BF3;        // state layout: E in one FP32 plane + two bf16 planes
@@ -437,6 +444,15 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 float I[4] = {cur.i.x, cur.i.y, cur.i.z, cur.i.w};
                 float ab[4] = {cur.b.x, cur.b.y, cur.b.z, cur.b.w};
                 float ad[4] = {cur.d.x, cur.d.y, cur.d.z, cur.d.w};
+                // per-node table: one broadcast 16-byte load per parameter and quad (the node index is warp-uniform)
+                float4 t_aee, t_aei, t_aii, t_kI, t_pmu, t_rho, t_rI, t_nmu, t_sI;
+                if (NODEPAR) {
+                    const float4* T = A.npar + (node0 >> 2);
+                    const int KQ = A.KG;
+                    t_aee = __ldg(T + kNpAee * KQ); t_aei = __ldg(T + kNpAei * KQ); t_aii = __ldg(T + kNpAii * KQ); t_kI = __ldg(T + kNpKI * KQ);
+                    t_pmu = __ldg(T + kNpPmu * KQ); t_rho = __ldg(T + kNpRhoE * KQ); t_rI = __ldg(T + kNpRI * KQ); t_nmu = __ldg(T + kNpNmu * KQ);
+                    t_sI = __ldg(T + kNpSigI2 * KQ);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int node = node0 + j;
@@ -447,13 +463,17 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                         else ad[j] = 0.f;
                     }
                     if (live && S.rec && sim < A.Bo) A.Ebuf[((size_t)S.row * N + node) * A.Bo + sim] = E[j];      // state BEFORE the update (WC:129-130)
-                    float xp = fmaf(c.sq, z[j], Pmu);
-                    xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(c.a_ee, E[j], xp)));
+                    const float p_aee = NODEPAR ? f4c(t_aee, j) : c.a_ee, p_aei = NODEPAR ? f4c(t_aei, j) : c.a_ei, p_aii = NODEPAR ? f4c(t_aii, j) : c.a_ii;
+                    const float p_pmu = NODEPAR ? f4c(t_pmu, j) : Pmu, p_nmu = NODEPAR ? f4c(t_nmu, j) : nmu, p_sI = NODEPAR ? f4c(t_sI, j) : c.sigI2;
+                    const float p_kI = NODEPAR ? f4c(t_kI, j) : c.kI, p_rI = NODEPAR ? f4c(t_rI, j) : c.rI;
+                    const float p_nkr = NODEPAR ? -S.kA * f4c(t_rho, j) : nkr;
+                    float xp = fmaf(c.sq, z[j], p_pmu);
+                    xp = fmaf(-ab[j], I[j], fmaf(-ad[j], I[j], fmaf(p_aee, E[j], xp)));
                     xp4[j] = __float_as_uint(xp);
-                    const float y = fmaf(-c.a_ii, I[j], fmaf(c.a_ei, E[j], nmu));
-                    const float SI = rcpf(1.0f + ex2f(y * c.sigI2));
-                    const float dn = fmaf(I[j], fmaf(E[j], S.kA, nkr), ad[j]);
-                    const float In = fmaf(c.kI, fmaf(fmaf(-c.rI, I[j], 1.0f), SI, -I[j]), I[j]);
+                    const float y = fmaf(-p_aii, I[j], fmaf(p_aei, E[j], p_nmu));
+                    const float SI = rcpf(1.0f + ex2f(y * p_sI));
+                    const float dn = fmaf(I[j], fmaf(E[j], S.kA, p_nkr), ad[j]);
+                    const float In = fmaf(p_kI, fmaf(fmaf(-p_rI, I[j], 1.0f), SI, -I[j]), I[j]);
                     I[j] = live ? In : 0.f;
                     ad[j] = live ? dn : 0.f;
                 }
@@ -509,6 +529,11 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 for (int h = 0; h < 2; ++h) {
                     float E[4] = {ce[h].x, ce[h].y, ce[h].z, ce[h].w};
                     if (!MIXED) { E[0] += ce[NE - 2 + h].x; E[1] += ce[NE - 2 + h].y; E[2] += ce[NE - 2 + h].z; E[3] += ce[NE - 2 + h].w; }
+                    float4 t_kE, t_rE;
+                    if (NODEPAR) {
+                        const float4* T = A.npar + ((node0 + 4 * h) >> 2);
+                        t_kE = __ldg(T + kNpKE * A.KG); t_rE = __ldg(T + kNpRE * A.KG);
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int node = node0 + 4 * h + j;
@@ -518,7 +543,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                         const float sg2 = HOMO ? sgh : fmaf(dsg, __ldg(A.mapS + node), sg0);
                         const float x = fmaf(Gi, coup, __uint_as_float(xp8[4 * h + j]));
                         const float SE = rcpf(1.0f + ex2f(x * sg2));
-                        const float e1 = fmaf(c.kE, fmaf(fmaf(-c.rE, E[j], 1.0f), SE, -E[j]), E[j]);
+                        const float p_kE = NODEPAR ? f4c(t_kE, j) : c.kE, p_rE = NODEPAR ? f4c(t_rE, j) : c.rE;
+                        const float e1 = fmaf(p_kE, fmaf(fmaf(-p_rE, E[j], 1.0f), SE, -E[j]), E[j]);
                         En[4 * h + j] = live ? e1 : 0.f;
                     }
                 }
@@ -617,8 +643,24 @@ __global__ void big_stage_maps_kernel(const double* mapG, const double* mapS, in
     mS[k] = (k < N && mapS) ? (float)mapS[k] : 1.f;
 }
 
+// node_params [NREM_NODE_PARAMS][N] float64 (a_ee a_ei a_ii tauE tauI P rhoE rE rI mu sigmaI a_ie_0) -> the float32 table of the NODEPAR
+// kernels, [kBigNpar][Kpad] with the derived quantities the step code uses (the same float32 expressions as make_const for scalars)
+__global__ void big_stage_npar_kernel(const double* np, int N, int Kpad, double dtSim, float* out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kpad) return;
+    const bool live = k < N;
+    auto at = [&](int row) { return live ? np[(size_t)row * N + k] : 1.0; };
+    const float P = (float)at(5), mu = (float)at(9);
+    out[kNpAee * Kpad + k] = (float)at(0); out[kNpAei * Kpad + k] = (float)at(1); out[kNpAii * Kpad + k] = (float)at(2);
+    out[kNpKE * Kpad + k] = (float)(dtSim / at(3)); out[kNpKI * Kpad + k] = (float)(dtSim / at(4));
+    out[kNpPmu * Kpad + k] = P - mu; out[kNpRhoE * Kpad + k] = (float)at(6); out[kNpRE * Kpad + k] = (float)at(7);
+    out[kNpRI * Kpad + k] = (float)at(8); out[kNpNmu * Kpad + k] = -mu; out[kNpSigI2 * Kpad + k] = (float)(-at(10) * 1.4426950408889634);
+    out[kNpA0 * Kpad + k] = (float)at(11);
+}
+
 // initial condition (netwWilsonCowanPlastic.py:90-99) into the images; every array was zeroed before
-__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, float4* A0, size_t plane, float4* I4, float4* ab4, float4* ad4) {
+__global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, float4* A0, size_t plane, float4* I4, float4* ab4, float4* ad4,
+                                const float* npar /* NULL or the per-node table: a_ie_0 per node */) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index [tile][kg][r]
     if (idx >= nf4) return;
     const int kg = (int)((idx / kTile) % KG);
@@ -631,7 +673,7 @@ __global__ void big_init_kernel(BatchConst c, int64_t nf4, int KG, int mixed, fl
         e[j] = live ? (mixed ? c.E0 : tf32_rn(c.E0)) : 0.f;
         l[j] = live ? (mixed == 2 ? c.E0 - __bfloat162float(__float2bfloat16_rn(c.E0)) : mixed ? c.E0 - tf32_trunc(c.E0) : c.E0 - e[j]) : 0.f;
         i[j] = live ? c.I0 : 0.f;
-        a[j] = live ? c.a0 : 0.f;
+        a[j] = live ? (npar ? npar[(size_t)kNpA0 * KG * 4 + kg * 4 + j] : c.a0) : 0.f;
     }
     A0[idx] = make_float4(e[0], e[1], e[2], e[3]);
     if (!mixed) {

@@ -296,9 +296,10 @@ def integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, map_id=No
 
 
 def big_integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, streams=None, kernel="auto", record=True,
-                      want_coupling=False, device=None):
+                      want_coupling=False, node_params=None, device=None):
     """Large-connectome integrator (BASELINE configs[4]; csrc/wc_big.cuh): any 16 <= nnodes <= 8192, one launch per Euler
     step.  Returns (E samples [nrec, N, B] or None, final [3, N, B]) and, with want_coupling, SC.E of the first step [N, B].
+    node_params: {name: length-N vector} for any of NODE_PARAMS (netwWilsonCowanPlastic.py:21; kernel "auto" / "bf3").
     `ops.last_integrate_ms()` gives the device time of the step launches."""
     dev = _device(device)
     N = p.nnodes
@@ -318,8 +319,10 @@ def big_integrate_f32(p, CM, G0, dG, sigma0, dsigma, mapG=None, mapS=None, strea
         d_E = torch.empty((max(nrec, 1), N, Bs), dtype=torch.float32, device=dev) if record and nrec > 0 else None
         d_fin = torch.empty((3, N, Bs), dtype=torch.float32, device=dev)
         d_cp = torch.empty((N, Bs), dtype=torch.float32, device=dev) if want_coupling else None
-        check(lib.nrem_big_integrate_f32(C.byref(p), KERNELS[kernel], _ptr(d_CM), _ptr(d_mG), _ptr(d_mS), _ptr(d[0]), _ptr(d[1]),
-                                         _ptr(d[2]), _ptr(d[3]), _ptr(d_st), B, nrec, _ptr(d_E), _ptr(d_fin), _ptr(d_cp), _stream()))
+        d_np = to_device(node_param_table(p, node_params), torch.float64, dev) if node_params else None
+        check(lib.nrem_big_integrate_f32_ex(C.byref(p), KERNELS[kernel], _ptr(d_CM), _ptr(d_mG), _ptr(d_mS), _ptr(d[0]), _ptr(d[1]),
+                                            _ptr(d[2]), _ptr(d[3]), _ptr(d_st), _ptr(d_np), B, nrec, _ptr(d_E), _ptr(d_fin), _ptr(d_cp),
+                                            _stream()))
         E = d_E[:, :, :B].cpu().numpy() if d_E is not None else None
         fin = d_fin[:, :, :B].cpu().numpy()
         if want_coupling:

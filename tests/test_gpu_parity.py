@@ -708,6 +708,48 @@ def test_sweep_beyond_128_nodes_vs_oracle(N, hetero, oracle_lib, monkeypatch):
     plan.close(); plan2.close()
 
 
+@pytest.mark.parametrize("N,B", [(300, 130), (136, 256)])
+def test_large_connectome_every_node_parameter_as_a_vector(N, B, oracle_lib):
+    """"Any of them can be redefined as a vector of length nnodes" (netwWilsonCowanPlastic.py:21) beyond 128 nodes: all twelve per-node
+    vectors through the large-connectome integrator (per-node table kernels of wc_big.cuh) against the NumPy oracle whose expressions
+    broadcast; scalars given as a table reproduce the scalar run bit for bit; and through a sweep plan (node_params=...)."""
+    from nremmodfc_b200 import ops, sweep
+    from oracle import bold_oracle, wc_oracle
+    rng = np.random.default_rng(N)
+    vec = {"a_ee": 3.5 + 0.2 * rng.random(N), "a_ei": 3.75 - 0.2 * rng.random(N), "a_ii": 0.1 * rng.random(N),
+           "tauE": 0.010 * (1 + 0.1 * rng.random(N)), "tauI": 0.020 * (1 + 0.1 * rng.random(N)), "P": 0.4 + 0.05 * rng.random(N),
+           "rhoE": 0.18 + 0.02 * rng.random(N), "rE": 0.5 + 0.05 * rng.random(N), "rI": 0.5 - 0.05 * rng.random(N),
+           "mu": 1.0 + 0.05 * rng.random(N), "sigmaI": 4.0 + 0.3 * rng.random(N), "a_ie_0": 2.5 + 0.2 * rng.random(N)}
+    SC = _random_sc(N, N + 3)
+    n1, n2, n3 = 20, 30, 60
+    p = ops.make_params(N, n1, n2, n3, seed=8)
+    dG, ds = rng.uniform(-0.1, 0.3, B), rng.uniform(-0.2, 0.2, B)
+    mG, mS = rng.uniform(0.5, 1.5, N), rng.uniform(0.8, 1.2, N)
+    streams = np.arange(B, dtype=np.uint64) + 3
+    args = (p, SC, np.full(B, 0.16), dG, np.full(B, 7.68), ds)
+    E, fin = ops.big_integrate_f32(*args, mG, mS, streams, node_params=vec)
+    po = wc_oracle.params(**vec)
+    for b in (0, 77, B - 1):
+        Yo, fo = wc_oracle.run(SC, 0.16 + dG[b] * mG, 7.68 + ds[b] * mS, n1, n2, n3, seed=8, streams=[int(streams[b])], p=po, return_final=True)
+        assert np.max(np.abs(E[:, :, b] - Yo[0, :, 0, :]) / np.abs(Yo[0, :, 0, :])) < 2e-4
+        assert np.max(np.abs(fin[:, :, b] - fo[0]) / np.abs(fo[0])) < 2e-4
+    # homogeneous call (no maps) with a table; scalars as a table == the scalar kernel bit for bit; a real table changes the result
+    E0, f0 = ops.big_integrate_f32(*args, None, None, streams)
+    E1, f1 = ops.big_integrate_f32(*args, None, None, streams, node_params={"P": np.full(N, p.P), "tauE": np.full(N, p.tauE)})
+    assert np.array_equal(E0, E1) and np.array_equal(f0, f1) and not np.allclose(E0, E)
+    with pytest.raises(Exception):
+        ops.big_integrate_f32(*args, None, None, streams, kernel="tc3", node_params=vec)
+    # sweep plan beyond 128 nodes with a table: same samples -> same FC as the oracle chain
+    p2 = ops.make_params(N, 100, 300, 4000, seed=8)
+    emp = np.stack([np.corrcoef(rng.normal(size=(N, 80)) + rng.normal(size=(1, 80))) for _ in range(2)])
+    out = sweep.sweep_gof(p2, SC, emp, 0.16, dG, 7.68, ds, streams, mapG=mG[None], mapS=mS[None], want_fc=True, node_params=vec,
+                          bold_f32=False, Neq=50, bold_downsamp=10, chunk_samples=64)
+    Eg, _ = ops.big_integrate_f32(p2, SC, np.full(B, 0.16), dG, np.full(B, 7.68), ds, mG, mS, streams, node_params=vec)
+    for b in (0, B - 1):
+        bold = bold_oracle.filt_decimate(oracle_lib.bold_sim(Eg[:, :, b].astype(np.float64), 0.04), 10, 50, 0.04)
+        assert np.max(np.abs(bold_oracle.fc(bold) - out["fc"][b])) < 1e-6
+
+
 def test_large_connectome_persistent_cluster_mode_is_bit_identical(monkeypatch):
     """NREM_BIG_PERSIST=1 runs the same step code inside one thread-block cluster per tile (barrier.cluster per step instead of a
     launch per step): the arithmetic is identical, so E samples and final state must match the per-step launches bit for bit."""
@@ -748,16 +790,18 @@ def test_large_connectome_cta_pair_mode_is_bit_identical(kernel, B, monkeypatch)
     assert np.array_equal(E0, E1) and np.array_equal(f0, f1)
 
 
-def test_large_connectome_matches_small_path_statistics(aal90):
+@pytest.mark.parametrize("big_kernel", ["tc3", "bf3"])
+def test_large_connectome_matches_small_path_statistics(big_kernel, aal90):
     """The per-step kernel and the register-resident kernel integrate the same model with the same noise: on AAL90 (N = 90,
-    which both accept) their float32 trajectories agree to rounding over a short horizon, incl. an a_ie recombination."""
+    which both accept) their float32 trajectories agree to rounding over a short horizon, incl. an a_ie recombination (for bf3: the
+    re-split of a_ie into a bf16 base and its FP32 remainder)."""
     from nremmodfc_b200 import ops
     p = ops.make_params(90, 100, 4200, 400, P=0.4, rhoE=0.18, seed=5)
     B = 128
     dG = np.linspace(-0.1, 0.02, B)
     st = np.arange(B, dtype=np.uint64) + 11
     E1, f1 = ops.integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=st, kernel="tc3")
-    E2, f2 = ops.big_integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=st, kernel="tc3")
+    E2, f2 = ops.big_integrate_f32(p, aal90["SC"], np.full(B, 0.16), dG, np.full(B, 7.68), np.zeros(B), streams=st, kernel=big_kernel)
     assert np.max(np.abs(E1[0] - E2[0]) / np.abs(E1[0])) < 5e-3          # 0.43 s of chaotic float32 dynamics
     assert np.max(np.abs(f1[2] - f2[2]) / np.abs(f1[2])) < 5e-3
 
