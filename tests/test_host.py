@@ -322,3 +322,27 @@ print("ok")
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_node_param_table_validation(built):
+    """{name: vector} -> [NREM_NODE_PARAMS, N] table of the per-node parameter kernels (netwWilsonCowanPlastic.py:21): names not given keep
+    the scalar of the parameter block, unknown names and wrong lengths are rejected before anything reaches the device."""
+    from nremmodfc_b200 import ops
+    p = ops.make_params(200, 1, 1, 20, P=0.37)
+    t = ops.node_param_table(p, {"tauE": np.linspace(0.009, 0.011, 200), "a_ie_0": 3.0})
+    assert t.shape == (len(ops.NODE_PARAMS), 200)
+    assert np.all(t[ops.NODE_PARAMS.index("P")] == 0.37) and np.all(t[ops.NODE_PARAMS.index("a_ie_0")] == 3.0)
+    assert t[ops.NODE_PARAMS.index("tauE"), -1] == 0.011
+    with pytest.raises(ValueError):
+        ops.node_param_table(p, {"G": np.ones(200)})              # G / sigmaE go through the maps, not through the table
+    with pytest.raises(ValueError):
+        ops.node_param_table(p, {"tauE": np.ones(90)})
+
+
+def test_oracle_metrics_beyond_128_nodes():
+    """The oracle side of the large-parcellation tests: FC / GoF restatements are size-agnostic (identity: corr 1, distance 0, SSIM 1)."""
+    from oracle import bold_oracle
+    rng = np.random.default_rng(3)
+    fc = bold_oracle.fc(rng.normal(size=(298, 200)) + rng.normal(size=(298, 1)))
+    assert fc.shape == (200, 200) and np.allclose(np.diag(fc), 1.0)
+    assert np.allclose(bold_oracle.get_all_metrics(fc, fc), [1.0, 0.0, 1.0, 0.0], atol=1e-12)
