@@ -414,7 +414,7 @@ static int big_layout(BigRun& R, const nrem_wc_params& p, int kernel, int B) {
     NREM_REQUIRE(R.k == 2 || R.k == 3 || R.k == 4 || R.k == 7, "kernel must be auto, tc, tc3, tcb or bf3");
     R.mixed = R.k == 4 ? 1 : (R.k == 7 ? 2 : 0);
     R.N = p.nnodes;
-    R.Kpad = (int)round_up(R.N, 4 * kBigKS); R.KG = R.Kpad / 4; R.slices = (R.N + kBigNT - 1) / kBigNT;
+    R.Kpad = (int)round_up(R.N, 4 * (R.k == 7 ? big_ks<5>() : kBigKS)); R.KG = R.Kpad / 4; R.slices = (R.N + kBigNT - 1) / kBigNT;
     // CTA pairs (cta_group::2, two 128-simulation tiles per M = 256 MMA) whenever the batch has an even number of tiles, or enough
     // tiles that one padding tile is cheap; NREM_BIG_PAIR=0 / 1 forces the choice (read per call: tests run both).  The persistent
     // cluster mode keeps single-CTA MMAs.

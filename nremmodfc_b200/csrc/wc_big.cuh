@@ -50,6 +50,11 @@ constexpr int kBigStages = 4;
 constexpr int kBigEpiWarps = 16;
 constexpr int kBigThreads = (2 + kBigEpiWarps) * 32;
 constexpr int kBigCols = kBigNT / (kBigEpiWarps / 4);     // accumulator columns per epilogue warp
+// bf3 can take more input nodes per stage (its stages are half as big per node): NREM_BIG_KS_BF3 four-node groups
+#ifndef NREM_BIG_KS_BF3
+#define NREM_BIG_KS_BF3 4
+#endif
+template <int MODE> __host__ __device__ constexpr int big_ks() { return MODE == 5 ? NREM_BIG_KS_BF3 : kBigKS; }
 constexpr uint32_t kBigAStage = kBigKS * kTile * 16;     // 8 KB per (hi | lo)
 constexpr uint32_t kBigBStage = kBigKS * kBigNT * 16;    // 16 KB per (hi | lo)
 constexpr uint32_t kBigLBO_A = kTile * 16;
@@ -66,13 +71,17 @@ constexpr uint32_t kBigIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(
 #endif
 constexpr int kBigStagesPair = NREM_BIG_STAGES_PAIR;
 template <int MODE, bool PAIR = false>
-__host__ __device__ constexpr uint32_t big_stage_bytes() { return ((MODE == 1 || MODE == 5) ? 1u : 2u) * (kBigAStage + (PAIR ? kBigBStage / 2 : kBigBStage)); }
+__host__ __device__ constexpr uint32_t big_stage_bytes() {
+    return ((MODE == 1 || MODE == 5) ? 1u : 2u) * (uint32_t)(big_ks<MODE>() / kBigKS) * (kBigAStage + (PAIR ? kBigBStage / 2 : kBigBStage));
+}
 // ring depth: bf3 stages are half as big as tcb's, so twice as many fit the same shared memory
 #ifndef NREM_BIG_STAGES_BF3_PAIR
 #define NREM_BIG_STAGES_BF3_PAIR 14
 #endif
 template <int MODE, bool PAIR = false>
-__host__ __device__ constexpr int big_stages() { return MODE == 5 ? (PAIR ? NREM_BIG_STAGES_BF3_PAIR : 9) : (PAIR ? kBigStagesPair : kBigStages); }
+__host__ __device__ constexpr int big_stages() {
+    return MODE == 5 ? (PAIR ? NREM_BIG_STAGES_BF3_PAIR : 9) * kBigKS / big_ks<5>() : (PAIR ? kBigStagesPair : kBigStages);
+}
 template <int MODE, bool PAIR = false>
 constexpr int big_smem_bytes() { return (int)(big_stages<MODE, PAIR>() * big_stage_bytes<MODE, PAIR>()) + 512; }
 constexpr uint32_t kBigIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBigNT >> 3) << 17) | ((uint32_t)((2 * kTile) >> 4) << 24);
@@ -233,15 +242,17 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     constexpr bool MIXED = MODE == 4 || BF3;        // state layout: E in one FP32 plane + two bf16 planes
     constexpr int NST = big_stages<MODE, PAIR>();
     constexpr int BROWS = PAIR ? kBigNT / 2 : kBigNT;              // B rows (output nodes) this CTA holds in shared memory
-    constexpr uint32_t BSTAGE = (uint32_t)kBigKS * BROWS * 16;     // bytes of one FP32 B stage
+    constexpr int KS = big_ks<MODE>();                             // four-node groups per pipeline stage
+    constexpr uint32_t ASTAGE = (uint32_t)KS * kTile * 16;          // bytes of one FP32 A stage (bf16 parts: half)
+    constexpr uint32_t BSTAGE = (uint32_t)KS * BROWS * 16;         // bytes of one FP32 B stage
     constexpr uint32_t LBO_B = (uint32_t)BROWS * 16;
     constexpr uint32_t STAGE = big_stage_bytes<MODE, PAIR>();
-    static_assert(STAGE == ((MODE == 1 || BF3) ? 1u : 2u) * (kBigAStage + BSTAGE), "stage size");
+    static_assert(STAGE == ((MODE == 1 || BF3) ? 1u : 2u) * (ASTAGE + BSTAGE), "stage size");
     constexpr uint32_t IDESC_TF32 = PAIR ? kBigIdescPair : kBigIdesc, IDESC_BF16 = PAIR ? kBigIdescBf16Pair : kBigIdescBf16;
     // stage layout   MODE 1: [A 8K][B 16K]      MODE 3: [Ah 8K][Al 8K][Bh 16K][Bl 16K]
     //                MODE 4: [Af 8K][Al bf16 4K][Ah bf16 4K][Bf 16K][Bh bf16 8K][Bl bf16 8K]        (PAIR: every B part is half as big)
     //                MODE 5: [Al bf16 4K][Ah bf16 4K][Bh bf16 8K][Bl bf16 8K]
-    constexpr uint32_t OFF_B = ((MODE == 1 || BF3) ? 1u : 2u) * kBigAStage;
+    constexpr uint32_t OFF_B = ((MODE == 1 || BF3) ? 1u : 2u) * ASTAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + NST * STAGE);
     uint64_t* empty = full + NST;
     uint64_t* accum = empty + NST;
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // grid (slices, tiles); the CTA-pair kernel is launched as (tiles, slices) with clusters (2, 1, 1) = tiles 2p, 2p+1 of a slice
     const int slice = PAIR ? blockIdx.y : blockIdx.x, tile = PAIR ? blockIdx.x : blockIdx.y;
-    const int KT = A.KG / kBigKS;
+    const int KT = A.KG / KS;
     const BatchConst& c = A.c;
     const int N = c.N;
 
@@ -299,21 +310,21 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 mbar_expect_tx(full + s, STAGE);
                 const uint32_t dst = base + (uint32_t)s * STAGE;
                 if (BF3) {
-                    bulk_g2s(dst, aL + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
-                    bulk_g2s(dst + kBigAStage / 2, aH + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
+                    bulk_g2s(dst, aL + (size_t)kt * (ASTAGE / 2), ASTAGE / 2, full + s);
+                    bulk_g2s(dst + ASTAGE / 2, aH + (size_t)kt * (ASTAGE / 2), ASTAGE / 2, full + s);
                     bulk_g2s(dst + OFF_B, bH + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
                     bulk_g2s(dst + OFF_B + BSTAGE / 2, bL + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
                     continue;
                 }
-                bulk_g2s(dst, a0 + (size_t)kt * kBigAStage, kBigAStage, full + s);
+                bulk_g2s(dst, a0 + (size_t)kt * ASTAGE, ASTAGE, full + s);
                 bulk_g2s(dst + OFF_B, b0 + (size_t)kt * BSTAGE, BSTAGE, full + s);
                 if (SPLIT) {
-                    bulk_g2s(dst + kBigAStage, a1 + (size_t)kt * kBigAStage, kBigAStage, full + s);
+                    bulk_g2s(dst + ASTAGE, a1 + (size_t)kt * ASTAGE, ASTAGE, full + s);
                     bulk_g2s(dst + OFF_B + BSTAGE, b1 + (size_t)kt * BSTAGE, BSTAGE, full + s);
                 }
                 if (MODE == 4) {
-                    bulk_g2s(dst + kBigAStage, aL + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
-                    bulk_g2s(dst + kBigAStage + kBigAStage / 2, aH + (size_t)kt * (kBigAStage / 2), kBigAStage / 2, full + s);
+                    bulk_g2s(dst + ASTAGE, aL + (size_t)kt * (ASTAGE / 2), ASTAGE / 2, full + s);
+                    bulk_g2s(dst + ASTAGE + ASTAGE / 2, aH + (size_t)kt * (ASTAGE / 2), ASTAGE / 2, full + s);
                     bulk_g2s(dst + OFF_B + BSTAGE, bH + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
                     bulk_g2s(dst + OFF_B + BSTAGE + BSTAGE / 2, bL + (size_t)kt * (BSTAGE / 2), BSTAGE / 2, full + s);
                 }
@@ -345,10 +356,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 tc_fence_after();
                 const uint32_t sa = base + (uint32_t)s * STAGE;
                 if (BF3) {
-                    const uint64_t aL = umma_desc(sa, kBigLBO_A, kSBO), aH = umma_desc(sa + kBigAStage / 2, kBigLBO_A, kSBO);
+                    const uint64_t aL = umma_desc(sa, kBigLBO_A, kSBO), aH = umma_desc(sa + ASTAGE / 2, kBigLBO_A, kSBO);
                     const uint64_t bH = umma_desc(sa + OFF_B, LBO_B, kSBO), bL = umma_desc(sa + OFF_B + BSTAGE / 2, LBO_B, kSBO);
 #pragma unroll
-                    for (int k16 = 0; k16 < kBigKS / 4; ++k16) {
+                    for (int k16 = 0; k16 < KS / 4; ++k16) {
                         const uint64_t da = (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), db = (uint64_t)(k16 * ((2 * LBO_B) >> 4));
                         if (PAIR) { umma_bf16_2(tmem_d, aH + da, bH + db, IDESC_BF16, acc); umma_bf16_2(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16_2(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
                         else { umma_bf16(tmem_d, aH + da, bH + db, IDESC_BF16, acc); umma_bf16(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
@@ -357,10 +368,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                     if (PAIR) umma_commit_2(empty + s); else umma_commit(empty + s);
                     continue;
                 }
-                const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO);
+                const uint64_t ad_hi = umma_desc(sa, kBigLBO_A, kSBO), ad_lo = umma_desc(sa + ASTAGE, kBigLBO_A, kSBO);
                 const uint64_t bd_hi = umma_desc(sa + OFF_B, LBO_B, kSBO), bd_lo = umma_desc(sa + OFF_B + BSTAGE, LBO_B, kSBO);
 #pragma unroll
-                for (int k8 = 0; k8 < kBigKS / 2; ++k8) {
+                for (int k8 = 0; k8 < KS / 2; ++k8) {
 #pragma unroll
                     for (int pass = 0; pass < (SPLIT ? 3 : 1); ++pass) {
                         const uint64_t a0 = (pass == 1) ? ad_lo : ad_hi;
@@ -373,10 +384,10 @@ __global__ void __launch_bounds__(kBigThreads, 1) wc_big_step_kernel(const BigAr
                 if (MODE == 4) {
                     // one K = 16 BF16 MMA per correction: the bf16 stage arrays are [2 eight-node groups][rows][16 B], i.e. the same
                     // core-matrix geometry (LBO = rows x 16 B, SBO = 128 B) as a K = 8 TF32 slice
-                    const uint64_t aL = umma_desc(sa + kBigAStage, kBigLBO_A, kSBO), aH = umma_desc(sa + kBigAStage + kBigAStage / 2, kBigLBO_A, kSBO);
+                    const uint64_t aL = umma_desc(sa + ASTAGE, kBigLBO_A, kSBO), aH = umma_desc(sa + ASTAGE + ASTAGE / 2, kBigLBO_A, kSBO);
                     const uint64_t bH = umma_desc(sa + OFF_B + BSTAGE, LBO_B, kSBO), bL = umma_desc(sa + OFF_B + BSTAGE + BSTAGE / 2, LBO_B, kSBO);
 #pragma unroll
-                    for (int k16 = 0; k16 < kBigKS / 4; ++k16) {
+                    for (int k16 = 0; k16 < KS / 4; ++k16) {
                         const uint64_t da = (uint64_t)(k16 * ((2 * kBigLBO_A) >> 4)), db = (uint64_t)(k16 * ((2 * LBO_B) >> 4));
                         if (PAIR) { umma_bf16_2(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16_2(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
                         else { umma_bf16(tmem_d, aL + da, bH + db, IDESC_BF16, 1); umma_bf16(tmem_d, aH + da, bL + db, IDESC_BF16, 1); }
